@@ -1,0 +1,301 @@
+// HBM-bound kernels of the F Lite denoise step: RMSNorm + adaLN modulate, standalone RoPE + QK-norm,
+// patch embedding, timestep embedding, unpatchify, varlen context packing, and the sampler's fused
+// CFG-combine + Euler update.  All vectorised 16-byte accesses, one warp per token row where a row
+// reduction is needed.  bf16 rounding points follow the reference op sequence.
+#pragma once
+
+#include "common.cuh"
+
+namespace flite {
+
+FLITE_DEVICE void unpack8(const uint4& v, float* f) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+FLITE_DEVICE uint4 pack8(const float* f) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                      pack_bf16x2(f[6], f[7]));
+}
+FLITE_DEVICE float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// y = RMSNorm_w(x) [* (1 + scale[s]) + shift[s]]           one warp per row, d % 256 == 0
+//   weight_mode 0: no weight            (f_lite/model.py:101-108, QK-norm style)
+//   weight_mode 1: Liger "llama" cast   bf16(x*rstd) * w in bf16      (model.py:238,283,292,299,437)
+//   weight_mode 2: reference RMSNorm    bf16(x*rstd*w) in fp32        (model.py:104-106, final_norm)
+//   modulate: n*(1+scale)+shift with a bf16 rounding after each op    (model.py:284,293,300,580)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+rmsnorm_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
+                        long long ldy, const __nv_bfloat16* __restrict__ w, int weight_mode,
+                        const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift,
+                        long long ld_mod, int rows_per_sample, int rows, int d, float eps) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+    const int nchunk = d >> 3;  // 16-byte chunks per row
+    float ssq = 0.f;
+    for (int c = lane; c < nchunk; c += 32) {
+        float f[8];
+        unpack8(__ldg(xr + c), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ssq += f[j] * f[j];
+    }
+    ssq = warp_sum(ssq);
+    const float rstd = rsqrtf(ssq / (float)d + eps);
+    const bool mod = scale != nullptr;
+    const long long s = (long long)(row / rows_per_sample) * ld_mod;
+    uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
+    for (int c = lane; c < nchunk; c += 32) {
+        float f[8], wv[8], sc[8], sh[8];
+        unpack8(__ldg(xr + c), f);
+        if (weight_mode != 0) unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), wv);
+        if (mod) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(scale + s) + c), sc);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(shift + s) + c), sh);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float n;
+            if (weight_mode == 1) n = bf16_round(bf16_round(f[j] * rstd) * wv[j]);
+            else if (weight_mode == 2) n = bf16_round(f[j] * rstd * wv[j]);
+            else n = bf16_round(f[j] * rstd);
+            if (mod) {
+                const float one_plus = bf16_round(1.0f + sc[j]);
+                n = bf16_round(n * one_plus);
+                n = n + sh[j];
+            }
+            f[j] = n;
+        }
+        yr[c] = pack8(f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Standalone RoPE + QK-RMSNorm, in place on packed projections [T, ld] (head_dim 256).
+// One warp per (token, head-slot); slots [0, n_rope_norm) are rotated + normalised, e.g. q and k heads
+// of a qkv buffer.  Kept as the unfused alternative to the GEMM's EPI_QKV_ROPE epilogue.
+// f_lite/model.py:166-180,403-414,92-108
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+rope_qknorm_kernel(__nv_bfloat16* __restrict__ buf, long long ld, int rows, int n_slots,
+                   const float* __restrict__ cos_t, const float* __restrict__ sin_t, int rows_per_sample,
+                   float eps) {
+    const long long w = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (w >= (long long)rows * n_slots) return;
+    const int row = (int)(w / n_slots), slot = (int)(w % n_slots);
+    const int lane = threadIdx.x & 31;
+    __nv_bfloat16* p = buf + (long long)row * ld + slot * 256;
+    // lane handles elements [4*lane, 4*lane+4) of the first half and the matching second-half elements
+    uint2 a = *reinterpret_cast<const uint2*>(p + 4 * lane);
+    uint2 b = *reinterpret_cast<const uint2*>(p + 128 + 4 * lane);
+    float x1[4] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y)};
+    float x2[4] = {bf16_lo(b.x), bf16_hi(b.x), bf16_lo(b.y), bf16_hi(b.y)};
+    if (cos_t != nullptr) {
+        const int pos = row % rows_per_sample;
+        const float4 cv = *reinterpret_cast<const float4*>(cos_t + (long long)pos * 128 + 4 * lane);
+        const float4 sv = *reinterpret_cast<const float4*>(sin_t + (long long)pos * 128 + 4 * lane);
+        const float cs[4] = {cv.x, cv.y, cv.z, cv.w}, sn[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float y1 = bf16_round(x1[j] * cs[j] + x2[j] * sn[j]);
+            const float y2 = bf16_round(x1[j] * (-sn[j]) + x2[j] * cs[j]);
+            x1[j] = y1; x2[j] = y2;
+        }
+    }
+    float ssq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ssq += x1[j] * x1[j] + x2[j] * x2[j];
+    ssq = warp_sum(ssq);
+    const float rstd = rsqrtf(ssq * (1.0f / 256.0f) + eps);
+    a = make_uint2(pack_bf16x2(x1[0] * rstd, x1[1] * rstd), pack_bf16x2(x1[2] * rstd, x1[3] * rstd));
+    b = make_uint2(pack_bf16x2(x2[0] * rstd, x2[1] * rstd), pack_bf16x2(x2[2] * rstd, x2[3] * rstd));
+    *reinterpret_cast<uint2*>(p + 4 * lane) = a;
+    *reinterpret_cast<uint2*>(p + 128 + 4 * lane) = b;
+}
+
+// ------------------------------------------------------------------------------------------
+// Patch embedding (Conv2d k = s = patch, f_lite/model.py:318-328) + register-token rows (model.py:535).
+// tokens[b*L + 16 + (hy*wp + wx), n] = bf16(sum_k patch[k] * W[n, k] + bias[n]),  k order (c, p1, p2)
+// tokens[b*L + r, n]                 = register_tokens[r, n]           r < n_reg
+// Block = 256 threads, PE_TOK tokens; each thread owns output columns tid, tid+256, ...
+// ------------------------------------------------------------------------------------------
+constexpr int PE_TOK = 32;
+template <int KDIM>
+__global__ void __launch_bounds__(256)
+patch_embed_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                   const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ reg_tokens,
+                   __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int P, int d, int n_reg) {
+    __shared__ float patch[PE_TOK][KDIM + 1];
+    const int hp = H / P, wp = W / P, hw = hp * wp, L = n_reg + hw;
+    const int tok0 = blockIdx.x * PE_TOK;           // index over B * L rows
+    for (int i = threadIdx.x; i < PE_TOK * KDIM; i += 256) {
+        const int t = i / KDIM, k = i % KDIM;
+        const int r = tok0 + t;
+        float v = 0.f;
+        if (r < B * L) {
+            const int b = r / L, l = r % L;
+            if (l >= n_reg) {
+                const int pi = l - n_reg, hy = pi / wp, wx = pi % wp;
+                const int c = k / (P * P), p1 = (k / P) % P, p2 = k % P;
+                v = __bfloat162float(x[(((long long)b * C + c) * H + hy * P + p1) * W + wx * P + p2]);
+            }
+        }
+        patch[t][k] = v;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < d; n += 256) {
+        float wr[KDIM];
+        const uint4* wp4 = reinterpret_cast<const uint4*>(w + (long long)n * KDIM);
+#pragma unroll
+        for (int j = 0; j < KDIM / 8; ++j) unpack8(__ldg(wp4 + j), wr + 8 * j);
+        const float bv = __bfloat162float(bias[n]);
+#pragma unroll 4
+        for (int t = 0; t < PE_TOK; ++t) {
+            const int r = tok0 + t;
+            if (r >= B * L) break;
+            const int l = r % L;
+            if (l < n_reg) {
+                out[(long long)r * d + n] = reg_tokens[(long long)l * d + n];
+            } else {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < KDIM; ++k) acc += patch[t][k] * wr[k];
+                out[(long long)r * d + n] = __float2bfloat16_rn(acc + bv);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Sinusoidal timestep embedding, f_lite/model.py:20-28,551:  arg = float(t*1000 [in t's dtype]) * freqs
+// emb = bf16(cat[cos(arg), sin(arg)]).  freqs[half] is computed by the host with the reference formula.
+// ------------------------------------------------------------------------------------------
+__global__ void timestep_embed_kernel(const float* __restrict__ t, int t_is_bf16, const float* __restrict__ freqs,
+                                      __nv_bfloat16* __restrict__ out, int B, int d) {
+    const int half = d / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, j = i % half;
+    float tv = t[b];
+    tv = t_is_bf16 ? bf16_round(bf16_round(tv) * 1000.0f) : tv * 1000.0f;
+    const float arg = tv * freqs[j];
+    out[(long long)b * d + j] = __float2bfloat16_rn(cosf(arg));
+    out[(long long)b * d + half + j] = __float2bfloat16_rn(sinf(arg));
+}
+
+// ------------------------------------------------------------------------------------------
+// Unpatchify, f_lite/model.py:577,583-590: "b (h w) (p1 p2 c) -> b c (h p1) (w p2)", register rows dropped.
+// ------------------------------------------------------------------------------------------
+__global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ tok, long long ldt,
+                                  __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int P, int n_reg) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * C * H * W;
+    if (i >= total) return;
+    const int wx_full = (int)(i % W), hy_full = (int)((i / W) % H), c = (int)((i / ((long long)W * H)) % C);
+    const int b = (int)(i / ((long long)W * H * C));
+    const int hp = H / P, wp = W / P, L = n_reg + hp * wp;
+    const int hy = hy_full / P, p1 = hy_full % P, wx = wx_full / P, p2 = wx_full % P;
+    const long long row = (long long)b * L + n_reg + hy * wp + wx;
+    out[i] = tok[row * ldt + (p1 * P + p2) * C + c];
+}
+
+// ------------------------------------------------------------------------------------------
+// Varlen context packing without a host sync, f_lite/model.py:31-64 (mask.sum -> cu_seqlens; nonzero ->
+// index_select).  One block per sequence computes the packed position of every valid token.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_scan_kernel(const float* __restrict__ mask, int Lc, int* __restrict__ pos, int* __restrict__ seqlens) {
+    __shared__ int warp_tot[8];
+    __shared__ int carry;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < Lc; base += 256) {
+        const int j = base + threadIdx.x;
+        const int valid = (j < Lc && mask[(long long)b * Lc + j] != 0.f) ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const int within = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        int off = carry;
+        for (int k = 0; k < wid; ++k) off += warp_tot[k];
+        if (j < Lc) pos[(long long)b * Lc + j] = valid ? off + within : -1;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int k = 0; k < 8; ++k) tot += warp_tot[k];
+            carry += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seqlens[b] = carry;
+}
+__global__ void cu_seqlens_kernel(const int* __restrict__ seqlens, int B, int* __restrict__ cu) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int acc = 0;
+        cu[0] = 0;
+        for (int b = 0; b < B; ++b) { acc += seqlens[b]; cu[b + 1] = acc; }
+    }
+}
+__global__ void __launch_bounds__(128)
+pack_rows_kernel(const __nv_bfloat16* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd,
+                 const int* __restrict__ pos, const int* __restrict__ cu, int B, int Lc, int d) {
+    const int r = blockIdx.x;  // source row in [0, B*Lc)
+    const int pp = pos[r];
+    if (pp < 0) return;
+    const int b = r / Lc;
+    const uint4* s = reinterpret_cast<const uint4*>(src + (long long)r * lds);
+    uint4* t = reinterpret_cast<uint4*>(dst + (long long)(cu[b] + pp) * ldd);
+    for (int c = threadIdx.x; c < (d >> 3); c += 128) t[c] = __ldg(s + c);
+}
+
+// ------------------------------------------------------------------------------------------
+// Sampler: fused CFG combine + Euler update (f_lite/pipeline.py:290,296-297; f_lite/train.py:596,599).
+//   v   = bf16(u + bf16(g * bf16(c - u)))                     (tensor ops in the model dtype)
+//   acc = acc + dt * v      bf16 accumulate (pipeline)  |  fp32 accumulate (train.py sample_images)
+//   lat = bf16(acc)                                            (next model input)
+// One pass, 8 elements per thread, 16-byte accesses.  acc_is_fp32 selects the accumulator dtype.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cfg_euler_kernel(void* __restrict__ acc, int acc_is_fp32, const __nv_bfloat16* __restrict__ v_uncond,
+                 const __nv_bfloat16* __restrict__ v_cond, float g, float dt, int do_cfg,
+                 __nv_bfloat16* __restrict__ lat_out, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+         i += (long long)gridDim.x * blockDim.x) {
+        float c[8], u[8], v[8], a[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(v_cond) + i), c);
+        if (do_cfg) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(v_uncond) + i), u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = bf16_round(u[j] + bf16_round(g * bf16_round(c[j] - u[j])));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = c[j];
+        }
+        if (acc_is_fp32) {
+            float4* ap = reinterpret_cast<float4*>(acc) + 2 * i;
+            float4 a0 = ap[0], a1 = ap[1];
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = a[j] + dt * v[j];
+            ap[0] = make_float4(a[0], a[1], a[2], a[3]);
+            ap[1] = make_float4(a[4], a[5], a[6], a[7]);
+        } else {
+            uint4* ap = reinterpret_cast<uint4*>(acc) + i;
+            unpack8(*ap, a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = bf16_round(a[j] + bf16_round(dt * v[j]));
+            *ap = pack8(a);
+        }
+        reinterpret_cast<uint4*>(lat_out)[i] = pack8(a);
+    }
+}
+
+}  // namespace flite

@@ -1,0 +1,384 @@
+// C ABI of libflite_b200.so (see include/flite_b200.h).  Host-side launch code only: argument checks,
+// TMA descriptor construction (driver entry point fetched at run time so the library also loads on a
+// machine without libcuda), kernel selection and launch.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/flite_b200.h"
+#include "attn_sm100.cuh"
+#include "elementwise.cuh"
+#include "gemm_sm100.cuh"
+
+using namespace flite;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) return fail(FLITE_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess) return fail(FLITE_ERR_CUDA, "launch: %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct TmapKey {
+    const void* ptr;
+    uint64_t rows, cols, ld;
+    uint32_t box_rows;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        h = h * 1000003u ^ k.rows;
+        h = h * 1000003u ^ k.cols;
+        h = h * 1000003u ^ k.ld;
+        h = h * 1000003u ^ k.box_rows;
+        return h;
+    }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+
+// 2-D bf16 row-major tensor [rows, cols] with row stride ld (elements); box = 64 columns (128 B, SWIZZLE_128B)
+// x box_rows rows; out-of-bounds elements read as zero.
+int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    TmapKey key{ptr, rows, cols, ld, box_rows};
+    {
+        std::lock_guard<std::mutex> g(g_tmap_mu);
+        auto it = g_tmap_cache.find(key);
+        if (it != g_tmap_cache.end()) {
+            *out = it->second;
+            return 0;
+        }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(FLITE_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16)
+        return fail(FLITE_ERR_INVALID, "TMA operand must be 16-byte aligned (ptr %p, ld %llu)", ptr,
+                    (unsigned long long)ld);
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FLITE_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    if (g_tmap_cache.size() > 65536) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *out);
+    return 0;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+template <int kCtaGroup, int BLOCK_N, int kStages, int kEpi>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+    using S = GemmSmem<kCtaGroup, BLOCK_N, kStages>;
+    auto kern = gemm_bf16_kernel<kCtaGroup, BLOCK_N, kStages, kEpi>;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        configured = true;
+    }
+    const int tile_m = 128 * kCtaGroup;
+    const int num_tiles = ((p.M + tile_m - 1) / tile_m) * (p.N / BLOCK_N);
+    int clusters = num_sms() / kCtaGroup;
+    if (clusters > num_tiles) clusters = num_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * kCtaGroup);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtaGroup;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    return 0;
+}
+
+template <int kCtaGroup, int BLOCK_N, int kStages>
+int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+    switch (epi) {
+        case EPI_STORE: return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_STORE>(ta, tb, p, s);
+        case EPI_GATED_RES: return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_GATED_RES>(ta, tb, p, s);
+        case EPI_SWIGLU:
+            if constexpr (BLOCK_N % 128 == 0) return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_SWIGLU>(ta, tb, p, s);
+            break;
+        case EPI_QKV_ROPE:
+            if constexpr (BLOCK_N == 256) return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_QKV_ROPE>(ta, tb, p, s);
+            break;
+    }
+    return fail(FLITE_ERR_INVALID, "epilogue %d not available for N-tile %d", epi, BLOCK_N);
+}
+
+}  // namespace
+
+extern "C" {
+
+int flite_abi_version(void) { return FLITE_ABI_VERSION; }
+const char* flite_last_error(void) { return g_err; }
+
+int flite_check_device(void) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(FLITE_ERR_UNSUPPORTED, "device is sm_%d%d, need sm_100", prop.major, prop.minor);
+    if (!get_encode_fn()) return fail(FLITE_ERR_UNSUPPORTED, "driver does not export cuTensorMapEncodeTiled");
+    return 0;
+}
+
+int flite_watchdog_status(unsigned int* code_out) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned int code = 0, zero = 0;
+    CUDA_TRY(cudaMemcpyFromSymbol(&code, g_flite_abort, sizeof(code)));
+    if (code_out) *code_out = code;
+    if (code != 0) {
+        CUDA_TRY(cudaMemcpyToSymbol(g_flite_abort, &zero, sizeof(zero)));
+        return fail(FLITE_ERR_WATCHDOG, "kernel barrier wait timed out: tag %u block %u", (code >> 16) & 0x7fff,
+                    code & 0xffff);
+    }
+    return 0;
+}
+
+int flite_cfg_euler(void* acc, int acc_is_fp32, const void* v_uncond, const void* v_cond, float guidance, float dt,
+                    int do_cfg, void* lat_out, int64_t numel, void* stream) {
+    if (!acc || !v_cond || !lat_out || (do_cfg && !v_uncond)) return fail(FLITE_ERR_INVALID, "cfg_euler: null pointer");
+    if (numel <= 0 || numel % 8) return fail(FLITE_ERR_INVALID, "cfg_euler: numel %lld must be a positive multiple of 8", (long long)numel);
+    const long long n8 = numel / 8;
+    int blocks = (int)((n8 + 255) / 256);
+    const int cap = num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    cfg_euler_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        acc, acc_is_fp32, (const __nv_bfloat16*)v_uncond, (const __nv_bfloat16*)v_cond, guidance, dt, do_cfg,
+        (__nv_bfloat16*)lat_out, n8);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int flite_rmsnorm_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w, int weight_mode,
+                           const void* scale, const void* shift, int64_t ld_mod, int rows_per_sample, int rows, int d,
+                           float eps, void* stream) {
+    if (!x || !y) return fail(FLITE_ERR_INVALID, "rmsnorm: null pointer");
+    if (d % 8 || ldx % 8 || ldy % 8) return fail(FLITE_ERR_INVALID, "rmsnorm: d/ld must be multiples of 8");
+    if (weight_mode != 0 && !w) return fail(FLITE_ERR_INVALID, "rmsnorm: weight_mode %d needs a weight", weight_mode);
+    if ((scale == nullptr) != (shift == nullptr)) return fail(FLITE_ERR_INVALID, "rmsnorm: scale and shift go together");
+    if (rows <= 0) return 0;
+    if (rows_per_sample <= 0) rows_per_sample = rows;
+    rmsnorm_modulate_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const __nv_bfloat16*)w, weight_mode,
+        (const __nv_bfloat16*)scale, (const __nv_bfloat16*)shift, ld_mod, rows_per_sample, rows, d, eps);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int flite_rope_qknorm(void* buf, int64_t ld, int rows, int n_slots, const float* cos_t, const float* sin_t,
+                      int rows_per_sample, float eps, void* stream) {
+    if (!buf) return fail(FLITE_ERR_INVALID, "rope_qknorm: null pointer");
+    if (ld % 8) return fail(FLITE_ERR_INVALID, "rope_qknorm: ld must be a multiple of 8");
+    if ((cos_t == nullptr) != (sin_t == nullptr)) return fail(FLITE_ERR_INVALID, "rope_qknorm: cos and sin go together");
+    if (rows <= 0 || n_slots <= 0) return 0;
+    if (rows_per_sample <= 0) rows_per_sample = rows;
+    const long long warps = (long long)rows * n_slots;
+    rope_qknorm_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)buf, ld, rows, n_slots, cos_t, sin_t, rows_per_sample, eps);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int flite_patch_embed(const void* x, const void* w, const void* bias, const void* reg_tokens, void* out, int B, int C,
+                      int H, int W, int P, int d, int n_reg, void* stream) {
+    if (!x || !w || !bias || !out || (n_reg > 0 && !reg_tokens)) return fail(FLITE_ERR_INVALID, "patch_embed: null pointer");
+    if (H % P || W % P) return fail(FLITE_ERR_INVALID, "patch_embed: H, W must be multiples of the patch size");
+    const int kdim = C * P * P;
+    const int rows = B * (n_reg + (H / P) * (W / P));
+    const int blocks = (rows + PE_TOK - 1) / PE_TOK;
+    auto args = [&](auto kern) {
+        kern<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
+                                                      (const __nv_bfloat16*)bias, (const __nv_bfloat16*)reg_tokens,
+                                                      (__nv_bfloat16*)out, B, C, H, W, P, d, n_reg);
+    };
+    if (kdim == 64) args(patch_embed_kernel<64>);
+    else if (kdim == 16) args(patch_embed_kernel<16>);
+    else return fail(FLITE_ERR_INVALID, "patch_embed: C*P*P = %d unsupported (16 or 64)", kdim);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int flite_timestep_embed(const float* t, int t_is_bf16, const float* freqs, void* out, int B, int d, void* stream) {
+    if (!t || !freqs || !out) return fail(FLITE_ERR_INVALID, "timestep_embed: null pointer");
+    if (d % 2) return fail(FLITE_ERR_INVALID, "timestep_embed: d must be even");
+    const int n = B * (d / 2);
+    timestep_embed_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, t_is_bf16, freqs, (__nv_bfloat16*)out, B, d);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int flite_unpatchify(const void* tok, int64_t ldt, void* out, int B, int C, int H, int W, int P, int n_reg,
+                     void* stream) {
+    if (!tok || !out) return fail(FLITE_ERR_INVALID, "unpatchify: null pointer");
+    const long long total = (long long)B * C * H * W;
+    unpatchify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)tok, ldt, (__nv_bfloat16*)out, B, C, H, W, P, n_reg);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int flite_pack_context(const void* src, int64_t lds, void* dst, int64_t ldd, const float* mask, int B, int Lc, int d,
+                       int* pos_ws, int* seqlens_ws, int* cu_seqlens, void* stream) {
+    if (!src || !dst || !mask || !pos_ws || !seqlens_ws || !cu_seqlens) return fail(FLITE_ERR_INVALID, "pack_context: null pointer");
+    if (d % 8 || lds % 8 || ldd % 8) return fail(FLITE_ERR_INVALID, "pack_context: d/ld must be multiples of 8");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (B <= 0 || Lc <= 0) return 0;
+    mask_scan_kernel<<<B, 256, 0, s>>>(mask, Lc, pos_ws, seqlens_ws);
+    cu_seqlens_kernel<<<1, 32, 0, s>>>(seqlens_ws, B, cu_seqlens);
+    pack_rows_kernel<<<B * Lc, 128, 0, s>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, pos_ws,
+                                           cu_seqlens, B, Lc, d);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                    const void* bias, int act, int epilogue, const void* resid, int64_t ldr, const void* gate,
+                    int64_t ld_gate, int rows_per_sample, const float* rope_cos, const float* rope_sin, int qk_cols,
+                    float eps, int variant, void* stream) {
+    if (!A || !W || !C) return fail(FLITE_ERR_INVALID, "gemm: null pointer");
+    if (M <= 0) return 0;
+    if (K <= 0 || K % 64) return fail(FLITE_ERR_INVALID, "gemm: K = %d must be a positive multiple of 64", K);
+    if (N <= 0 || N % 64) return fail(FLITE_ERR_INVALID, "gemm: N = %d must be a positive multiple of 64", N);
+    if (lda % 8 || ldw % 8 || ldc % 8) return fail(FLITE_ERR_INVALID, "gemm: lda/ldw/ldc must be multiples of 8");
+    if (epilogue < 0 || epilogue > 3) return fail(FLITE_ERR_INVALID, "gemm: unknown epilogue %d", epilogue);
+    if (epilogue == EPI_GATED_RES && (!resid || !gate || ldr % 8 || ld_gate % 8))
+        return fail(FLITE_ERR_INVALID, "gemm: gated-residual epilogue needs resid and gate (ld %% 8 == 0)");
+    if ((epilogue == EPI_SWIGLU || epilogue == EPI_QKV_ROPE) && N % 256)
+        return fail(FLITE_ERR_INVALID, "gemm: epilogue %d needs N %% 256 == 0", epilogue);
+    if (epilogue == EPI_QKV_ROPE && ((rope_cos == nullptr) != (rope_sin == nullptr) || qk_cols % 256))
+        return fail(FLITE_ERR_INVALID, "gemm: bad RoPE arguments");
+    if (rows_per_sample <= 0) rows_per_sample = M;
+
+    if (variant == FLITE_GEMM_AUTO) {
+        if (epilogue == EPI_QKV_ROPE) variant = (M > 128) ? FLITE_GEMM_2CTA_N256 : FLITE_GEMM_1CTA_N256;
+        else if (N % 256 == 0 && M > 128) variant = FLITE_GEMM_2CTA_N256;
+        else if (N % 128 == 0) variant = FLITE_GEMM_1CTA_N128;
+        else variant = FLITE_GEMM_1CTA_N64;
+    }
+    int block_n = 0, cg = 1;
+    switch (variant) {
+        case FLITE_GEMM_1CTA_N256: block_n = 256; break;
+        case FLITE_GEMM_2CTA_N256: block_n = 256; cg = 2; break;
+        case FLITE_GEMM_1CTA_N128: block_n = 128; break;
+        case FLITE_GEMM_1CTA_N64: block_n = 64; break;
+        default: return fail(FLITE_ERR_INVALID, "gemm: unknown variant %d", variant);
+    }
+    if (N % block_n) return fail(FLITE_ERR_INVALID, "gemm: N = %d not a multiple of the N-tile %d", N, block_n);
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K;
+    p.C = (__nv_bfloat16*)C; p.ldc = ldc;
+    p.bias = (const __nv_bfloat16*)bias; p.act = act;
+    p.resid = (const __nv_bfloat16*)resid; p.ldr = ldr;
+    p.gate = (const __nv_bfloat16*)gate; p.ld_gate = ld_gate;
+    p.rows_per_sample = rows_per_sample;
+    p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.qk_cols = qk_cols; p.eps = eps;
+
+    CUtensorMap ta, tb;
+    int rc = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128);
+    if (rc) return rc;
+    rc = make_tmap(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(block_n / cg));
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (variant) {
+        case FLITE_GEMM_1CTA_N256: return dispatch_epi<1, 256, 4>(epilogue, ta, tb, p, s);
+        case FLITE_GEMM_2CTA_N256: return dispatch_epi<2, 256, 6>(epilogue, ta, tb, p, s);
+        case FLITE_GEMM_1CTA_N128: return dispatch_epi<1, 128, 6>(epilogue, ta, tb, p, s);
+        case FLITE_GEMM_1CTA_N64: return dispatch_epi<1, 64, 8>(epilogue, ta, tb, p, s);
+    }
+    return fail(FLITE_ERR_INVALID, "gemm: unreachable");
+}
+
+int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                           int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
+                           const int* cu_q, const int* cu_k, int B, int H, int max_q, float softmax_scale,
+                           void* stream) {
+    if (!q || !k || !v || !out || !cu_q || !cu_k) return fail(FLITE_ERR_INVALID, "attention: null pointer");
+    if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || q_col0 % 8 || k_col0 % 8 || v_col0 % 8)
+        return fail(FLITE_ERR_INVALID, "attention: strides / column offsets must be multiples of 8");
+    if (B <= 0 || H <= 0 || max_q <= 0 || rows_q <= 0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        configured = true;
+    }
+    CUtensorMap tq, tk, tv;
+    int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)ldq, (uint64_t)ldq, 128);
+    if (rc) return rc;
+    rc = make_tmap(&tk, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldk, (uint64_t)ldk, 128);
+    if (rc) return rc;
+    rc = make_tmap(&tv, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldv, (uint64_t)ldv, 128);
+    if (rc) return rc;
+    AttnParams p;
+    p.cu_q = cu_q; p.cu_k = cu_k;
+    p.out = (__nv_bfloat16*)out; p.ldo = ldo;
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+    p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    dim3 grid((max_q + 127) / 128, H, B);
+    attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//
+//   warp 0      : TMA producer (A / W tiles -> 128B-swizzled smem ring, mbarrier full/empty)
+//   warp 1      : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM
+//   warps 2..5  : epilogue (tcgen05.ld -> registers -> fused math -> global), one output row per thread
+//
+// kCtaGroup == 2 pairs two SMs (cluster of 2) on one 256 x BLOCK_N tile with tcgen05.mma.cta_group::2:
+// each CTA stages its own 128 rows of A and half of the W tile, the leader CTA issues the MMAs and
+// multicasts the commits to both CTAs' barriers.
+//
+// Replaces the cuBLASLt calls behind nn.Linear in the reference (f_lite/model.py:151-156,162,212,267,
+// 436,448-454,472,475) and fuses what the reference runs as separate elementwise kernels:
+//   EPI_STORE     : (+bias) [SiLU]                          model.py:162,189,448-452
+//   EPI_GATED_RES : x + (acc) * gate[sample]                model.py:289,294-297,301
+//   EPI_SWIGLU    : silu(gate) * up on interleaved columns  liger swiglu, model.py:267
+//   EPI_QKV_ROPE  : +bias, 2-D RoPE, QK-RMSNorm per head     model.py:162-183,403-414,92-108
+#pragma once
+
+#include "common.cuh"
+
+namespace flite {
+
+enum GemmEpilogue : int { EPI_STORE = 0, EPI_GATED_RES = 1, EPI_SWIGLU = 2, EPI_QKV_ROPE = 3 };
+
+struct GemmParams {
+    int M, N, K;
+    __nv_bfloat16* C;
+    long long ldc;
+    const __nv_bfloat16* bias;   // [N] or nullptr
+    int act;                     // EPI_STORE: 0 none, 1 SiLU after the bf16 rounding of (acc + bias)
+    const __nv_bfloat16* resid;  // EPI_GATED_RES: [M, ldr]
+    long long ldr;
+    const __nv_bfloat16* gate;   // EPI_GATED_RES: gate[(row / rows_per_sample) * ld_gate + col]
+    long long ld_gate;
+    int rows_per_sample;
+    // EPI_QKV_ROPE: columns are (k in {q,k,v}, head, 256); rope tables [rows_per_sample, 128] fp32
+    const float* rope_cos;
+    const float* rope_sin;
+    int qk_cols;                 // columns [0, qk_cols) get RoPE (if tables != null) + RMSNorm; rest plain
+    float eps;
+};
+
+constexpr int GEMM_BLOCK_K = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int kCtaGroup, int BLOCK_N, int kStages>
+struct GemmSmem {
+    static constexpr int BN_CTA = BLOCK_N / kCtaGroup;
+    static constexpr int A_BYTES = 128 * GEMM_BLOCK_K * 2;
+    static constexpr int B_BYTES = BN_CTA * GEMM_BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = kStages * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <int kCtaGroup, int BLOCK_N, int kStages, int kEpi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+    using S = GemmSmem<kCtaGroup, BLOCK_N, kStages>;
+    constexpr int TILE_M = 128 * kCtaGroup;
+    constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+    static_assert(2 * BLOCK_N <= 512, "accumulators are double-buffered in TMEM");
+    static_assert(BLOCK_N % 32 == 0, "epilogue works on 32-column chunks");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0;
+    const bool is_leader = cta_rank == 0;
+
+    if (warp_idx == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp_idx == 1) {
+        if (elect_one()) {
+            for (int i = 0; i < kStages; ++i) {
+                mbar_init(&full_bar[i], 1);
+                mbar_init(&empty_bar[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&tmem_full_bar[i], 1);
+                mbar_init(&tmem_empty_bar[i], 4 * kCtaGroup);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<kCtaGroup>(tmem_ptr_smem, TMEM_COLS);
+    }
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_m_tiles = (p.M + TILE_M - 1) / TILE_M;
+    const int num_n_tiles = p.N / BLOCK_N;
+    const int num_tiles = num_m_tiles * num_n_tiles;
+    const int num_kb = p.K / GEMM_BLOCK_K;
+    const int cluster_id = blockIdx.x / kCtaGroup;
+    const int num_clusters = gridDim.x / kCtaGroup;
+
+    if (warp_idx == 0) {
+        // ================================ TMA producer ================================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m0 = (tile % num_m_tiles) * TILE_M + (int)cta_rank * 128;
+                const int n0 = (tile / num_m_tiles) * BLOCK_N + (int)cta_rank * S::BN_CTA;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait<kCtaGroup == 2>(&empty_bar[stage], phase ^ 1, 1);
+                    uint8_t* sa = smem + stage * S::STAGE_BYTES;
+                    uint8_t* sb = sa + S::A_BYTES;
+                    if constexpr (kCtaGroup == 1) {
+                        mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+                    } else {
+                        if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+                        tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], 0, kb * GEMM_BLOCK_K, m0);
+                        tma_load_2d_cg2(sb, &tmap_b, &full_bar[stage], 0, kb * GEMM_BLOCK_K, n0);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp_idx == 1) {
+        // ================================ MMA issuer ================================
+        if (is_leader && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait<kCtaGroup == 2>(&tmem_empty_bar[acc], acc_phase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait<kCtaGroup == 2>(&full_bar[stage], phase, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint32_t sb = sa + S::A_BYTES;
+                    const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+                        // +32 bytes (= 16 bf16) along K inside the 128B swizzle atom
+                        umma_ss<kCtaGroup>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if constexpr (kCtaGroup == 1) umma_commit(&empty_bar[stage]);
+                    else umma_commit_cg2(&empty_bar[stage], 0x3);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                if constexpr (kCtaGroup == 1) umma_commit(&tmem_full_bar[acc]);
+                else umma_commit_cg2(&tmem_full_bar[acc], 0x3);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ epilogue ================================
+        const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
+        const int lane = (int)lane_id();
+        int it = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m0 = (tile % num_m_tiles) * TILE_M + (int)cta_rank * 128;
+            const int n0 = (tile / num_m_tiles) * BLOCK_N;
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            mbar_wait<kCtaGroup == 2>(&tmem_full_bar[acc], acc_phase, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+
+            if constexpr (kEpi == EPI_STORE || kEpi == EPI_GATED_RES) {
+                const __nv_bfloat16* gate_row = nullptr;
+                if constexpr (kEpi == EPI_GATED_RES)
+                    gate_row = p.gate + (long long)((row_ok ? row : 0) / p.rows_per_sample) * p.ld_gate;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_x32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    const int col = n0 + c * 32;
+                    uint32_t outp[16];
+                    uint32_t bias_p[16];
+                    if (p.bias != nullptr) {
+                        const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 v = __ldg(bp + j);
+                            bias_p[4 * j] = v.x; bias_p[4 * j + 1] = v.y; bias_p[4 * j + 2] = v.z; bias_p[4 * j + 3] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) bias_p[j] = 0;
+                    }
+                    if constexpr (kEpi == EPI_STORE) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a = bf16_round(__uint_as_float(r[2 * j]) + bf16_lo(bias_p[j]));
+                            float b = bf16_round(__uint_as_float(r[2 * j + 1]) + bf16_hi(bias_p[j]));
+                            if (p.act == 1) { a = silu_f(a); b = silu_f(b); }
+                            outp[j] = pack_bf16x2(a, b);
+                        }
+                    } else {
+                        uint32_t res_p[16], gate_p[16];
+                        if (row_ok) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (long long)row * p.ldr + col);
+                            const uint4* gp = reinterpret_cast<const uint4*>(gate_row + col);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 v = __ldg(rp + j);
+                                res_p[4 * j] = v.x; res_p[4 * j + 1] = v.y; res_p[4 * j + 2] = v.z; res_p[4 * j + 3] = v.w;
+                                uint4 g = __ldg(gp + j);
+                                gate_p[4 * j] = g.x; gate_p[4 * j + 1] = g.y; gate_p[4 * j + 2] = g.z; gate_p[4 * j + 3] = g.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) { res_p[j] = 0; gate_p[j] = 0; }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            // reference rounding points: y = bf16(acc+b); yg = bf16(y*gate); x' = bf16(x+yg)
+                            float a = bf16_round(__uint_as_float(r[2 * j]) + bf16_lo(bias_p[j]));
+                            float b = bf16_round(__uint_as_float(r[2 * j + 1]) + bf16_hi(bias_p[j]));
+                            a = bf16_round(a * bf16_lo(gate_p[j]));
+                            b = bf16_round(b * bf16_hi(gate_p[j]));
+                            outp[j] = pack_bf16x2(bf16_lo(res_p[j]) + a, bf16_hi(res_p[j]) + b);
+                        }
+                    }
+                    if (row_ok) {
+                        uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            cp[j] = make_uint4(outp[4 * j], outp[4 * j + 1], outp[4 * j + 2], outp[4 * j + 3]);
+                    }
+                }
+            } else if constexpr (kEpi == EPI_SWIGLU) {
+                // weight rows are interleaved in groups of 64: [gate 64 | up 64] per 128 accumulator columns
+                static_assert(kEpi != EPI_SWIGLU || BLOCK_N % 128 == 0, "SwiGLU epilogue needs 128-column groups");
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 64; ++c) {
+                    const int grp = c >> 1, half = c & 1;
+                    uint32_t g[32], u[32];
+                    tmem_ld_x32(taddr + grp * 128 + half * 32, g);
+                    tmem_ld_x32(taddr + grp * 128 + 64 + half * 32, u);
+                    tmem_ld_wait();
+                    uint32_t outp[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        // liger swiglu: silu(bf16(gate).fp32).bf16 * bf16(up)
+                        float g0 = bf16_round(__uint_as_float(g[2 * j])), g1 = bf16_round(__uint_as_float(g[2 * j + 1]));
+                        float u0 = bf16_round(__uint_as_float(u[2 * j])), u1 = bf16_round(__uint_as_float(u[2 * j + 1]));
+                        g0 = bf16_round(silu_f(g0));
+                        g1 = bf16_round(silu_f(g1));
+                        outp[j] = pack_bf16x2(g0 * u0, g1 * u1);
+                    }
+                    if (row_ok) {
+                        const int col = n0 / 2 + grp * 64 + half * 32;
+                        uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            cp[j] = make_uint4(outp[4 * j], outp[4 * j + 1], outp[4 * j + 2], outp[4 * j + 3]);
+                    }
+                }
+            } else if constexpr (kEpi == EPI_QKV_ROPE) {
+                // One 256-column tile = one head of q, k or v; one thread = one token row of that head.
+                static_assert(kEpi != EPI_QKV_ROPE || BLOCK_N == 256, "QKV epilogue needs one head per tile");
+                const bool do_norm = n0 < p.qk_cols;
+                const bool do_rope = do_norm && p.rope_cos != nullptr;
+                const int pos = (row_ok ? row : 0) % p.rows_per_sample;
+                const float4* cosr = reinterpret_cast<const float4*>(p.rope_cos + (long long)pos * 128);
+                const float4* sinr = reinterpret_cast<const float4*>(p.rope_sin + (long long)pos * 128);
+                float ssq = 0.f;
+                // pass 1: bias, RoPE (pairs j, j+128), sum of squares of the bf16-rounded rotated values
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t x1[32], x2[32];
+                    tmem_ld_x32(taddr + c * 32, x1);
+                    tmem_ld_x32(taddr + 128 + c * 32, x2);
+                    tmem_ld_wait();
+                    uint32_t o1[16], o2[16];
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int e0 = c * 32 + hf * 16;  // element offset inside the 128-wide half
+                        float cs[16], sn[16], ba[16], bb[16];
+                        if (do_rope) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 cv = __ldg(cosr + (e0 >> 2) + j), sv = __ldg(sinr + (e0 >> 2) + j);
+                                cs[4 * j] = cv.x; cs[4 * j + 1] = cv.y; cs[4 * j + 2] = cv.z; cs[4 * j + 3] = cv.w;
+                                sn[4 * j] = sv.x; sn[4 * j + 1] = sv.y; sn[4 * j + 2] = sv.z; sn[4 * j + 3] = sv.w;
+                            }
+                        }
+                        if (p.bias != nullptr) {
+                            const uint4* b1p = reinterpret_cast<const uint4*>(p.bias + n0 + e0);
+                            const uint4* b2p = reinterpret_cast<const uint4*>(p.bias + n0 + 128 + e0);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint4 v1 = __ldg(b1p + j), v2 = __ldg(b2p + j);
+                                ba[8 * j] = bf16_lo(v1.x); ba[8 * j + 1] = bf16_hi(v1.x); ba[8 * j + 2] = bf16_lo(v1.y);
+                                ba[8 * j + 3] = bf16_hi(v1.y); ba[8 * j + 4] = bf16_lo(v1.z); ba[8 * j + 5] = bf16_hi(v1.z);
+                                ba[8 * j + 6] = bf16_lo(v1.w); ba[8 * j + 7] = bf16_hi(v1.w);
+                                bb[8 * j] = bf16_lo(v2.x); bb[8 * j + 1] = bf16_hi(v2.x); bb[8 * j + 2] = bf16_lo(v2.y);
+                                bb[8 * j + 3] = bf16_hi(v2.y); bb[8 * j + 4] = bf16_lo(v2.z); bb[8 * j + 5] = bf16_hi(v2.z);
+                                bb[8 * j + 6] = bf16_lo(v2.w); bb[8 * j + 7] = bf16_hi(v2.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) { ba[j] = 0.f; bb[j] = 0.f; }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const int jj = hf * 16 + j;
+                            float a0 = bf16_round(__uint_as_float(x1[jj]) + ba[j]);
+                            float a1 = bf16_round(__uint_as_float(x1[jj + 1]) + ba[j + 1]);
+                            float b0 = bf16_round(__uint_as_float(x2[jj]) + bb[j]);
+                            float b1 = bf16_round(__uint_as_float(x2[jj + 1]) + bb[j + 1]);
+                            if (do_rope) {
+                                // model.py:412-413: y1 = x1*cos + x2*sin ; y2 = x1*(-sin) + x2*cos (fp32, then cast)
+                                const float y10 = bf16_round(a0 * cs[j] + b0 * sn[j]);
+                                const float y20 = bf16_round(a0 * (-sn[j]) + b0 * cs[j]);
+                                const float y11 = bf16_round(a1 * cs[j + 1] + b1 * sn[j + 1]);
+                                const float y21 = bf16_round(a1 * (-sn[j + 1]) + b1 * cs[j + 1]);
+                                a0 = y10; b0 = y20; a1 = y11; b1 = y21;
+                            }
+                            ssq += a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1;
+                            o1[jj >> 1] = pack_bf16x2(a0, a1);
+                            o2[jj >> 1] = pack_bf16x2(b0, b1);
+                        }
+                    }
+                    if (!do_norm && row_ok) {
+                        uint4* cp1 = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + n0 + c * 32);
+                        uint4* cp2 = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + n0 + 128 + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            cp1[j] = make_uint4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+                            cp2[j] = make_uint4(o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
+                        }
+                    } else if (do_norm) {
+                        // park the rotated bf16 pairs back in TMEM (same columns, packed) for pass 2
+                        tmem_st_x16(taddr + c * 32, o1);
+                        tmem_st_x16(taddr + 128 + c * 32, o2);
+                    }
+                }
+                if (do_norm) {
+                    tmem_st_wait();
+                    const float rstd = rsqrtf(ssq * (1.0f / 256.0f) + p.eps);
+#pragma unroll 1
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t v[16];
+                        tmem_ld_x16(taddr + (c >> 2) * 128 + (c & 3) * 32, v);
+                        tmem_ld_wait();
+                        uint32_t o[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(bf16_lo(v[j]) * rstd, bf16_hi(v[j]) * rstd);
+                        if (row_ok) {
+                            uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + n0 + (c >> 2) * 128 +
+                                                                 (c & 3) * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) cp[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) {
+                if constexpr (kCtaGroup == 1) mbar_arrive(&tmem_empty_bar[acc]);
+                else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ================================ teardown ================================
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+    if (warp_idx == 1) tmem_dealloc<kCtaGroup>(tmem_base, TMEM_COLS);
+}
+
+}  // namespace flite

@@ -1,0 +1,197 @@
+"""torch-tensor front end of the C ABI (``include/flite_b200.h``).
+
+PyTorch is used for device memory and streams only; every function here launches a hand-written
+sm_100a kernel from ``libflite_b200.so`` on torch's current CUDA stream.  No fallbacks.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_GATED_RES, EPI_QKV_ROPE, EPI_STORE, EPI_SWIGLU, GEMM_AUTO)
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, name: str, dtype=BF16, rows_contig=True):
+    if not t.is_cuda:
+        raise _lib.FliteError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.FliteError(f"{name}: expected {dtype}, got {t.dtype}")
+    if rows_contig and t.dim() >= 1 and t.stride(-1) != 1:
+        raise _lib.FliteError(f"{name}: innermost dimension must be contiguous")
+
+
+def cfg_euler(acc: torch.Tensor, v_uncond: Optional[torch.Tensor], v_cond: torch.Tensor, guidance: float,
+              dt: float, lat_out: torch.Tensor, do_cfg: bool = True) -> None:
+    """acc += dt * (u + g (c - u)); lat_out = bf16(acc).  f_lite/pipeline.py:290,296-297."""
+    lib = _lib.load()
+    _chk(v_cond, "v_cond")
+    _chk(lat_out, "lat_out")
+    if do_cfg:
+        _chk(v_uncond, "v_uncond")
+    if acc.dtype not in (BF16, torch.float32):
+        raise _lib.FliteError("acc must be bf16 or fp32")
+    for t in (acc, v_cond, lat_out) + ((v_uncond,) if do_cfg else ()):
+        if not t.is_contiguous():
+            raise _lib.FliteError("cfg_euler operands must be contiguous")
+    _lib.check(lib.flite_cfg_euler(acc.data_ptr(), int(acc.dtype == torch.float32), _ptr(v_uncond) if do_cfg else None,
+                                   v_cond.data_ptr(), float(guidance), float(dt), int(do_cfg), lat_out.data_ptr(),
+                                   acc.numel(), _stream()), "cfg_euler")
+
+
+def rmsnorm_modulate(x: torch.Tensor, weight: Optional[torch.Tensor], weight_mode: int,
+                     scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+                     rows_per_sample: int = 0, eps: float = 1e-6, out: Optional[torch.Tensor] = None):
+    """x [rows, d]; scale/shift are [B, d] views into the modulation matrix (same row stride)."""
+    lib = _lib.load()
+    _chk(x, "x")
+    rows, d = x.shape
+    if out is None:
+        out = torch.empty((rows, d), dtype=BF16, device=x.device)
+    ld_mod = 0
+    if scale is not None:
+        _chk(scale, "scale")
+        _chk(shift, "shift")
+        ld_mod = scale.stride(0)
+        if shift.stride(0) != ld_mod:
+            raise _lib.FliteError("scale and shift must share a row stride")
+    _lib.check(lib.flite_rmsnorm_modulate(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), _ptr(weight),
+                                          weight_mode, _ptr(scale), _ptr(shift), ld_mod, rows_per_sample, rows, d,
+                                          eps, _stream()), "rmsnorm_modulate")
+    return out
+
+
+def rope_qknorm_(buf: torch.Tensor, n_slots: int, cos: Optional[torch.Tensor], sin: Optional[torch.Tensor],
+                 rows_per_sample: int = 0, eps: float = 1e-6) -> None:
+    lib = _lib.load()
+    _chk(buf, "buf")
+    if cos is not None:
+        _chk(cos, "cos", torch.float32)
+        _chk(sin, "sin", torch.float32)
+    _lib.check(lib.flite_rope_qknorm(buf.data_ptr(), buf.stride(0), buf.shape[0], n_slots, _ptr(cos), _ptr(sin),
+                                     rows_per_sample, eps, _stream()), "rope_qknorm")
+
+
+def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, reg_tokens: torch.Tensor, patch: int,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias"), (reg_tokens, "register_tokens")):
+        _chk(t, n)
+        if not t.is_contiguous():
+            raise _lib.FliteError(f"{n} must be contiguous")
+    B, C, H, W = x.shape
+    d = weight.shape[0]
+    n_reg = reg_tokens.shape[-2]
+    rows = B * (n_reg + (H // patch) * (W // patch))
+    if out is None:
+        out = torch.empty((rows, d), dtype=BF16, device=x.device)
+    _lib.check(lib.flite_patch_embed(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), reg_tokens.data_ptr(),
+                                     out.data_ptr(), B, C, H, W, patch, d, n_reg, _stream()), "patch_embed")
+    return out
+
+
+def timestep_embed(t_f32: torch.Tensor, t_is_bf16: bool, freqs: torch.Tensor, d: int,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(t_f32, "t", torch.float32)
+    _chk(freqs, "freqs", torch.float32)
+    B = t_f32.numel()
+    if out is None:
+        out = torch.empty((B, d), dtype=BF16, device=t_f32.device)
+    _lib.check(lib.flite_timestep_embed(t_f32.data_ptr(), int(t_is_bf16), freqs.data_ptr(), out.data_ptr(), B, d,
+                                        _stream()), "timestep_embed")
+    return out
+
+
+def unpatchify(tok: torch.Tensor, B: int, C: int, H: int, W: int, patch: int, n_reg: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _chk(tok, "tok")
+    if out is None:
+        out = torch.empty((B, C, H, W), dtype=BF16, device=tok.device)
+    _lib.check(lib.flite_unpatchify(tok.data_ptr(), tok.stride(0), out.data_ptr(), B, C, H, W, patch, n_reg,
+                                    _stream()), "unpatchify")
+    return out
+
+
+def pack_context(src: torch.Tensor, mask_f32: torch.Tensor):
+    """src [B, Lc, d] bf16, mask [B, Lc] fp32 -> (packed [B*Lc, d] zero-padded, cu_seqlens int32 [B+1])."""
+    lib = _lib.load()
+    _chk(src, "src")
+    _chk(mask_f32, "mask", torch.float32)
+    B, Lc, d = src.shape
+    src2 = src.reshape(B * Lc, d)
+    dst = torch.zeros((B * Lc, d), dtype=BF16, device=src.device)
+    pos = torch.empty(B * Lc, dtype=torch.int32, device=src.device)
+    seqlens = torch.empty(B, dtype=torch.int32, device=src.device)
+    cu = torch.empty(B + 1, dtype=torch.int32, device=src.device)
+    _lib.check(lib.flite_pack_context(src2.data_ptr(), src2.stride(0), dst.data_ptr(), dst.stride(0),
+                                      mask_f32.contiguous().data_ptr(), B, Lc, d, pos.data_ptr(), seqlens.data_ptr(),
+                                      cu.data_ptr(), _stream()), "pack_context")
+    return dst, cu
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = 0,
+         epilogue: int = EPI_STORE, resid: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+         rows_per_sample: int = 0, rope_cos: Optional[torch.Tensor] = None, rope_sin: Optional[torch.Tensor] = None,
+         qk_cols: int = 0, eps: float = 1e-6, variant: int = GEMM_AUTO, out: Optional[torch.Tensor] = None):
+    """out = epilogue(a @ w.T); a [M, K], w [N, K] (nn.Linear layout), bf16."""
+    lib = _lib.load()
+    _chk(a, "a")
+    _chk(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=BF16, device=a.device)
+    _chk(out, "out")
+    for t, n in ((bias, "bias"), (resid, "resid"), (gate, "gate")):
+        if t is not None:
+            _chk(t, n)
+    for t, n in ((rope_cos, "rope_cos"), (rope_sin, "rope_sin")):
+        if t is not None:
+            _chk(t, n, torch.float32)
+    _lib.check(lib.flite_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
+                                   out.stride(0), M, N, K, _ptr(bias), act, epilogue, _ptr(resid),
+                                   resid.stride(0) if resid is not None else 0, _ptr(gate),
+                                   gate.stride(0) if gate is not None else 0, rows_per_sample, _ptr(rope_cos),
+                                   _ptr(rope_sin), qk_cols, eps, variant, _stream()), "gemm_bf16")
+    return out
+
+
+def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: torch.Tensor, cu_k: torch.Tensor,
+                     num_heads: int, max_q: int, softmax_scale: float, out: Optional[torch.Tensor] = None):
+    """q [Tq, >= H*256] / k, v [Tk, >= H*256] are (possibly strided column) views of projection buffers."""
+    lib = _lib.load()
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, n)
+    _chk(cu_q, "cu_q", torch.int32)
+    _chk(cu_k, "cu_k", torch.int32)
+    Tq = q.shape[0]
+    if out is None:
+        out = torch.empty((Tq, num_heads * 256), dtype=BF16, device=q.device)
+    B = cu_q.numel() - 1
+    _lib.check(lib.flite_attention_varlen(q.data_ptr(), q.stride(0), Tq, 0, k.data_ptr(), k.stride(0), k.shape[0], 0,
+                                          v.data_ptr(), v.stride(0), 0, out.data_ptr(), out.stride(0),
+                                          cu_q.data_ptr(), cu_k.data_ptr(), B, num_heads, max_q,
+                                          float(softmax_scale), _stream()), "attention_varlen")
+    return out
+
+
+def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
+    """[inter, d] x2 -> [2*inter, d] with rows interleaved in groups of 64 ([g 64 | u 64] per 128 rows) so that
+    one accumulator tile holds matching gate / up columns for the EPI_SWIGLU epilogue."""
+    inter, d = gate_w.shape
+    assert inter % 64 == 0
+    return torch.stack([gate_w.view(inter // 64, 64, d), up_w.view(inter // 64, 64, d)], dim=1).reshape(2 * inter, d).contiguous()

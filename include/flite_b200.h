@@ -1,0 +1,115 @@
+/* flite_b200.h -- C ABI of libflite_b200.so: hand-written sm_100a kernels for the F Lite denoise step.
+ *
+ * The reference (sippycoder/f-lite) has no native layer: every op below replaces a
+ * Python call site in /root/reference/f_lite/model.py or the sampler loop in
+ * /root/reference/f_lite/pipeline.py; the citation on each entry point is the reference line(s) whose
+ * arithmetic it reproduces.  See INTEGRATION.md for the ctypes binding a maintainer adds on the
+ * reference side.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers (bf16 unless stated), caller-owned; the library allocates nothing
+ *   - ld* are row strides in ELEMENTS; rows must be 16-byte aligned
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered, never synchronise and are
+ *     CUDA-graph capturable
+ *   - return 0 on success, a negative FLITE_ERR_* otherwise; flite_last_error() gives the reason
+ *   - sm_100a only; there is no fallback path
+ */
+#ifndef FLITE_B200_H
+#define FLITE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLITE_ABI_VERSION 1
+
+#define FLITE_OK 0
+#define FLITE_ERR_INVALID (-1)   /* bad argument (shape / alignment / null)             */
+#define FLITE_ERR_CUDA (-2)      /* CUDA runtime or driver error                         */
+#define FLITE_ERR_UNSUPPORTED (-3) /* device is not sm_100 / required driver symbol missing */
+#define FLITE_ERR_WATCHDOG (-4)  /* a kernel barrier wait timed out (protocol bug)        */
+
+/* GEMM epilogues (flite_gemm_bf16) */
+#define FLITE_EPI_STORE 0      /* C = act(A W^T + bias)                         model.py:162,189,436,448-454,472,475 */
+#define FLITE_EPI_GATED_RES 1  /* C = resid + (A W^T + bias) * gate[sample]     model.py:289,294-297,301              */
+#define FLITE_EPI_SWIGLU 2     /* C = silu(A Wg^T) * (A Wu^T), W = interleave64(Wg, Wu)  model.py:267 (LigerSwiGLUMLP) */
+#define FLITE_EPI_QKV_ROPE 3   /* +bias, 2-D RoPE, per-head RMSNorm on q/k heads  model.py:162-183,403-414,92-108      */
+
+/* GEMM kernel variants */
+#define FLITE_GEMM_AUTO 0
+#define FLITE_GEMM_1CTA_N256 1
+#define FLITE_GEMM_2CTA_N256 2
+#define FLITE_GEMM_1CTA_N128 3
+#define FLITE_GEMM_1CTA_N64 4
+
+int flite_abi_version(void);
+const char* flite_last_error(void);
+
+/* 0 if cuda:current is sm_100 and the driver exports cuTensorMapEncodeTiled, else FLITE_ERR_UNSUPPORTED */
+int flite_check_device(void);
+
+/* Synchronises the device and reports (and clears) the kernel watchdog word; 0 = no barrier timed out. */
+int flite_watchdog_status(unsigned int* code_out);
+
+/* Sampler: fused CFG combine + Euler update.            pipeline.py:290,296-297 / train.py:596,599
+ *   v = u + g*(c-u) (skipped if !do_cfg: v = c);  acc += dt*v;  lat_out = bf16(acc)
+ *   acc is bf16 (acc_is_fp32 = 0, FLitePipeline semantics) or fp32 (= 1, train.py sample_images). */
+int flite_cfg_euler(void* acc, int acc_is_fp32, const void* v_uncond, const void* v_cond, float guidance,
+                    float dt, int do_cfg, void* lat_out, int64_t numel, void* stream);
+
+/* y = RMSNorm(x)[*w] [*(1+scale[s]) + shift[s]], s = row / rows_per_sample.   model.py:238,283-284,292-293,299-300,437,579-580
+ *   weight_mode 0 none | 1 Liger "llama" casting | 2 reference RMSNorm (fp32 weight multiply)
+ *   scale/shift may be NULL (no modulation); they index a [B, ld_mod] modulation matrix */
+int flite_rmsnorm_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w, int weight_mode,
+                           const void* scale, const void* shift, int64_t ld_mod, int rows_per_sample,
+                           int rows, int d, float eps, void* stream);
+
+/* In-place RoPE + QK-RMSNorm on head slots [0, n_slots) of buf[rows, ld] (head_dim 256).  model.py:166-180
+ *   cos/sin: fp32 [rows_per_sample, 128] or NULL (no rotation, cross-attention)          model.py:197 */
+int flite_rope_qknorm(void* buf, int64_t ld, int rows, int n_slots, const float* cos_t, const float* sin_t,
+                      int rows_per_sample, float eps, void* stream);
+
+/* Patch embedding + register tokens -> tokens[B*(n_reg + hw), d].                         model.py:318-328,535 */
+int flite_patch_embed(const void* x, const void* w, const void* bias, const void* reg_tokens, void* out,
+                      int B, int C, int H, int W, int P, int d, int n_reg, void* stream);
+
+/* Sinusoidal timestep embedding; t is fp32 on device, t_is_bf16 reproduces `timesteps*1000` in bf16.  model.py:20-28,551 */
+int flite_timestep_embed(const float* t, int t_is_bf16, const float* freqs, void* out, int B, int d,
+                         void* stream);
+
+/* tokens[B*L, ldt] (first P*P*C columns) -> out (B, C, H, W), register rows dropped.      model.py:577,583-590 */
+int flite_unpatchify(const void* tok, int64_t ldt, void* out, int B, int C, int H, int W, int P, int n_reg,
+                     void* stream);
+
+/* Varlen packing of context rows by a 0/1 mask, no host sync.                            model.py:31-64,530
+ *   mask fp32 [B, Lc]; pos_ws int32 [B*Lc] and seqlens_ws int32 [B] are workspaces;
+ *   cu_seqlens int32 [B+1] out; dst [>= B*Lc, ldd] must be zero-initialised by the caller */
+int flite_pack_context(const void* src, int64_t lds, void* dst, int64_t ldd, const float* mask, int B, int Lc,
+                       int d, int* pos_ws, int* seqlens_ws, int* cu_seqlens, void* stream);
+
+/* C[M, *] = epilogue(A[M,K] W[N,K]^T).  bf16 in, fp32 accumulate in TMEM (tcgen05), bf16 out.
+ *   Requirements: K % 64 == 0, N % 64 == 0 (N % 256 == 0 for SWIGLU / QKV_ROPE), lda/ldw/ldc % 8 == 0.
+ *   bias [N] or NULL; act: 0 none, 1 SiLU (EPI_STORE only)
+ *   EPI_GATED_RES: resid [M, ldr], gate row = gate + (row / rows_per_sample) * ld_gate
+ *   EPI_SWIGLU   : C has N/2 columns
+ *   EPI_QKV_ROPE : columns [0, qk_cols) are 256-wide heads that get RoPE (rope_cos/sin fp32
+ *                  [rows_per_sample, 128], may be NULL) and RMSNorm(eps); the rest is bias only */
+int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N,
+                    int K, const void* bias, int act, int epilogue, const void* resid, int64_t ldr,
+                    const void* gate, int64_t ld_gate, int rows_per_sample, const float* rope_cos,
+                    const float* rope_sin, int qk_cols, float eps, int variant, void* stream);
+
+/* Varlen non-causal flash attention, head_dim 256.                                        model.py:203-211
+ *   q[rows_q, ldq] head h at columns q_col0 + 256 h (same for k, v); cu_q / cu_k int32 [B+1] on device;
+ *   out[rows_q, ldo] head-major columns; max_q = longest query sequence (host value). */
+int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                           int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out,
+                           int64_t ldo, const int* cu_q, const int* cu_k, int B, int H, int max_q,
+                           float softmax_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLITE_B200_H */
