@@ -5,3 +5,7 @@ Drop-in for ``f_lite.DiT`` (``/root/reference/f_lite/model.py``) and the sampler
 hand-written CUDA kernels in ``csrc/`` behind the C ABI declared in ``include/flite_b200.h``.
 """
 __version__ = "0.1.0"
+
+from ._lib import FliteError  # noqa: E402,F401
+from .model import DiT  # noqa: E402,F401
+from .pipeline import APGConfig, FLitePipeline, FLitePipelineOutput, denoise, denoise_step  # noqa: E402,F401

@@ -183,7 +183,9 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, int t_is_bf16
     if (i >= B * half) return;
     const int b = i / half, j = i % half;
     float tv = t[b];
-    tv = t_is_bf16 ? bf16_round(bf16_round(tv) * 1000.0f) : tv * 1000.0f;
+    // t_is_bf16: 0 = fp32 timesteps, 1 = bf16 timesteps (t*1000 rounded to bf16), 2 = caller already scaled
+    if (t_is_bf16 == 1) tv = bf16_round(bf16_round(tv) * 1000.0f);
+    else if (t_is_bf16 == 0) tv = tv * 1000.0f;
     const float arg = tv * freqs[j];
     out[(long long)b * d + j] = __float2bfloat16_rn(cosf(arg));
     out[(long long)b * d + half + j] = __float2bfloat16_rn(sinf(arg));

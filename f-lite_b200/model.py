@@ -1,0 +1,355 @@
+"""Drop-in ``DiT`` for the F Lite denoise path, running on hand-written sm_100a kernels.
+
+Mirrors ``/root/reference/f_lite/model.py``:
+
+* same constructor keywords and defaults (model.py:419-433), ``.config.<kw>`` access (diffusers
+  ``register_to_config`` semantics), and the *same state-dict keys and shapes*  so
+  ``new.load_state_dict(ref.state_dict())`` is the weight hand-off;
+* ``forward(x, context, context_attn_mask, timesteps)`` (model.py:525-526); the legacy 3-argument call
+  ``forward(x, context, timesteps)`` that ``FLitePipeline.__call__`` still makes (pipeline.py:271,293)
+  is accepted too (mask := all ones);
+* inference only (``torch.no_grad``), bf16 only -- there is no CPU or PyTorch fallback: every op is a
+  kernel from ``libflite_b200.so``.
+
+What is fused relative to the reference graph: RMSNorm+adaLN modulate (K5/K6),
+QKV bias + RoPE + QK-norm in the GEMM epilogue (K1/K7/K9), gated residual adds in the GEMM epilogue
+(K2/K8), SiLU*up in the gate/up GEMM epilogue (K3), no pack/unpack copies or host syncs (K14), per-sample
+modulation never materialised per token (K6), RoPE table per (h, w) cached (K15), context projection /
+K,V hoisted out of the step loop (K13).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import (EPI_GATED_RES, EPI_QKV_ROPE, EPI_STORE, EPI_SWIGLU, GEMM_AUTO, FliteError)
+
+N_REGISTER = 16  # model.py:446,535,540
+
+
+class _Config(dict):
+    """dict with attribute access, like diffusers' FrozenDict behind ``register_to_config``."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+class _NormWeight(nn.Module):
+    """Holds ``weight`` only (LigerRMSNorm / RMSNorm state-dict layout, model.py:92-99,238)."""
+
+    def __init__(self, dim: int, has_weight: bool = True):
+        super().__init__()
+        if has_weight:
+            self.weight = nn.Parameter(torch.ones(dim))
+        else:
+            self.weight = None
+
+
+class Attention(nn.Module):
+    """Parameter container with the reference's names (model.py:133-158)."""
+
+    def __init__(self, dim: int, num_heads: int, qkv_bias: bool, is_self_attn: bool):
+        super().__init__()
+        assert dim % num_heads == 0
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.is_self_attn = is_self_attn
+        if is_self_attn:
+            self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        else:
+            self.q = nn.Linear(dim, dim, bias=qkv_bias)
+            self.context_kv = nn.Linear(dim, dim * 2, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim, bias=False)
+
+
+class _SwiGLU(nn.Module):
+    """LigerSwiGLUMLP parameter layout (model.py:262-267,312-314)."""
+
+    def __init__(self, hidden: int, inter: int):
+        super().__init__()
+        self.gate_proj = nn.Linear(hidden, inter, bias=False)
+        self.up_proj = nn.Linear(hidden, inter, bias=False)
+        self.down_proj = nn.Linear(inter, hidden, bias=False)
+
+
+class DiTBlock(nn.Module):
+    """model.py:226-267."""
+
+    def __init__(self, hidden_size, num_heads, do_cross_attn, mlp_ratio, qkv_bias):
+        super().__init__()
+        self.norm1 = _NormWeight(hidden_size)
+        self.self_attn = Attention(hidden_size, num_heads, qkv_bias, True)
+        if do_cross_attn:
+            self.norm2 = _NormWeight(hidden_size)
+            self.cross_attn = Attention(hidden_size, num_heads, qkv_bias, False)
+        else:
+            self.norm2 = None
+            self.cross_attn = None
+        self.norm3 = _NormWeight(hidden_size)
+        self.mlp = _SwiGLU(hidden_size, int(hidden_size * mlp_ratio))
+
+
+class PatchEmbed(nn.Module):
+    """model.py:318-322."""
+
+    def __init__(self, patch_size, in_channels, embed_dim):
+        super().__init__()
+        self.patch_proj = nn.Conv2d(in_channels, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.patch_size = patch_size
+
+
+def _rope_table(head_dim: int, h: int, w: int, base: float, n_reg: int, round_bf16: bool):
+    """cos/sin [n_reg + h*w, head_dim/2] fp32, values as the reference module holds them
+    (model.py:334-386; the buffers are bf16 after ``model.to(bf16)``).
+    Built with the same CPU torch ops as the reference constructor so the table is bit-identical."""
+    dim = head_dim // 2
+    inv = torch.tensor([1.0 / (base ** (i / dim)) for i in range(0, dim, 2)], dtype=torch.float32)
+    fh = torch.outer(torch.arange(h, dtype=torch.float32), inv).unsqueeze(1).repeat(1, w, 1)
+    fw = torch.outer(torch.arange(w, dtype=torch.float32), inv).unsqueeze(0).repeat(h, 1, 1)
+    f = torch.cat([fh, fw], 2).reshape(h * w, dim)
+    cos, sin = f.cos(), f.sin()
+    if round_bf16:
+        cos, sin = cos.bfloat16().float(), sin.bfloat16().float()
+    cos = torch.cat([torch.ones(n_reg, dim), cos], 0)
+    sin = torch.cat([torch.zeros(n_reg, dim), sin], 0)
+    return cos.contiguous(), sin.contiguous()
+
+
+class DiT(nn.Module):
+    def __init__(
+        self,
+        in_channels=4,
+        patch_size=2,
+        hidden_size=1152,
+        depth=28,
+        num_heads=16,
+        mlp_ratio=4.0,
+        cross_attn_input_size=128,
+        train_bias_and_rms=True,
+        use_rope=True,
+        gradient_checkpoint=False,
+        dynamic_softmax_temperature=False,
+        rope_base=10000,
+    ):
+        super().__init__()
+        self.config = _Config(
+            in_channels=in_channels, patch_size=patch_size, hidden_size=hidden_size, depth=depth,
+            num_heads=num_heads, mlp_ratio=mlp_ratio, cross_attn_input_size=cross_attn_input_size,
+            train_bias_and_rms=train_bias_and_rms, use_rope=use_rope, gradient_checkpoint=gradient_checkpoint,
+            dynamic_softmax_temperature=dynamic_softmax_temperature, rope_base=rope_base,
+        )
+        if hidden_size % num_heads or hidden_size // num_heads != 256:
+            raise FliteError("the sm_100a attention kernel is built for head_dim 256 "
+                             "(F Lite uses num_heads = hidden_size // 256, f_lite/train.py:690)")
+        if not use_rope:
+            raise FliteError("use_rope=False (learned positional embedding, model.py:444,546) is not on the "
+                             "F Lite hot path and is not implemented")
+        self.context_proj = nn.Linear(cross_attn_input_size, hidden_size)
+        self.context_norm = _NormWeight(hidden_size)
+        self.patch_embed = PatchEmbed(patch_size, in_channels, hidden_size)
+        self.register_tokens = nn.Parameter(torch.randn(1, N_REGISTER, hidden_size))
+        self.time_embed = nn.Sequential(
+            nn.Linear(hidden_size, 4 * hidden_size), nn.SiLU(), nn.Linear(4 * hidden_size, hidden_size))
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 9 * hidden_size, bias=True))
+        self.adaLN_modulation[-1].weight.data.zero_()
+        self.adaLN_modulation[-1].bias.data.zero_()
+        self.blocks = nn.ModuleList([
+            DiTBlock(hidden_size, num_heads, (idx % 4 == 0 or idx < 8), mlp_ratio, train_bias_and_rms)
+            for idx in range(depth)
+        ])
+        self.final_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 2 * hidden_size, bias=True))
+        self.final_norm = _NormWeight(hidden_size, has_weight=train_bias_and_rms)
+        self.final_proj = nn.Linear(hidden_size, patch_size * patch_size * in_channels)
+        for t in (self.final_modulation[-1].weight, self.final_modulation[-1].bias, self.final_proj.weight,
+                  self.final_proj.bias):
+            nn.init.zeros_(t)
+        # host-side caches (not part of the state dict)
+        self._rope_cache = {}
+        self._ws = {}
+        self._gu_cache = {}
+        self._ctx_cache = None
+        self._freqs = None
+        self.hoist_context = True
+        self.gemm_variant = GEMM_AUTO
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def dtype(self):
+        return self.context_proj.weight.dtype
+
+    @property
+    def device(self):
+        return self.context_proj.weight.device
+
+    def _check_ready(self):
+        w = self.context_proj.weight
+        if not w.is_cuda:
+            raise FliteError("flite_b200.DiT runs on CUDA (sm_100a) only; call .to('cuda') -- there is no CPU path")
+        if w.dtype != torch.bfloat16:
+            raise FliteError("flite_b200.DiT computes in bf16; call .to(torch.bfloat16)")
+
+    def _rope(self, h, w, device):
+        key = (h, w, str(device))
+        if key not in self._rope_cache:
+            hd = self.config.hidden_size // self.config.num_heads
+            cos, sin = _rope_table(hd, h, w, self.config.rope_base, N_REGISTER, round_bf16=True)
+            self._rope_cache[key] = (cos.to(device), sin.to(device))
+        return self._rope_cache[key]
+
+    def _gate_up(self, i, blk):
+        g, u = blk.mlp.gate_proj.weight, blk.mlp.up_proj.weight
+        key = (g.data_ptr(), g._version, u.data_ptr(), u._version)
+        hit = self._gu_cache.get(i)
+        if hit is None or hit[0] != key:
+            hit = (key, ops.interleave_gate_up(g.detach(), u.detach()))
+            self._gu_cache[i] = hit
+        return hit[1]
+
+    def _buf(self, name, shape, device):
+        key = (name, tuple(shape))
+        b = self._ws.get(key)
+        if b is None or b.device != device:
+            b = torch.empty(shape, dtype=torch.bfloat16, device=device)
+            self._ws[key] = b
+        return b
+
+    # ------------------------------------------------------------------ context (t-independent, K13)
+    def prepare_context(self, context: torch.Tensor, mask: Optional[torch.Tensor]):
+        """context_proj -> context_norm -> varlen pack -> per cross block K (normed) / V.
+        model.py:527-530,190-197.  Independent of the timestep, so computed once per prompt batch."""
+        cfg = self.config
+        d = cfg.hidden_size
+        B, Lc, ci = context.shape
+        ctx2 = context.reshape(B * Lc, ci)
+        if ctx2.dtype != torch.bfloat16:
+            ctx2 = ctx2.to(torch.bfloat16)
+        c = ops.gemm(ctx2, self.context_proj.weight, self.context_proj.bias, variant=self.gemm_variant)
+        c = ops.rmsnorm_modulate(c, self.context_norm.weight, 1)
+        if mask is None:
+            mask_f = torch.ones((B, Lc), dtype=torch.float32, device=context.device)
+        else:
+            mask_f = mask.to(torch.float32)
+        packed, cu_k = ops.pack_context(c.view(B, Lc, d), mask_f)
+        kvs = {}
+        for i, blk in enumerate(self.blocks):
+            if blk.cross_attn is None:
+                continue
+            lin = blk.cross_attn.context_kv
+            kvs[i] = ops.gemm(packed, lin.weight, lin.bias, epilogue=EPI_QKV_ROPE, qk_cols=d,
+                              variant=self.gemm_variant)
+        return SimpleNamespace(kvs=kvs, cu_k=cu_k, B=B, Lc=Lc)
+
+    def _context(self, context, mask):
+        if not self.hoist_context:
+            return self.prepare_context(context, mask)
+        key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype,
+               None if mask is None else (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype),
+               tuple((p.data_ptr(), p._version) for p in (self.context_proj.weight, self.context_norm.weight)))
+        if self._ctx_cache is None or self._ctx_cache[0] != key:
+            # keep references to the keyed tensors so their storage cannot be recycled under the cache
+            self._ctx_cache = (key, self.prepare_context(context, mask), context, mask)
+        return self._ctx_cache[1]
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x, context, context_attn_mask=None, timesteps=None):
+        if timesteps is None:  # legacy call form dit(x, context, t)  (pipeline.py:271,293)
+            if context_attn_mask is None:
+                raise TypeError("forward() missing timesteps")
+            timesteps, context_attn_mask = context_attn_mask, None
+        self._check_ready()
+        cfg = self.config
+        d, p, nh = cfg.hidden_size, cfg.patch_size, cfg.num_heads
+        dev = x.device
+        B, C, H, W = x.shape
+        hp, wp = H // p, W // p
+        L = N_REGISTER + hp * wp
+        T = B * L
+        v = self.gemm_variant
+
+        ctx = self._context(context, context_attn_mask)
+        if ctx.B != B:
+            raise FliteError(f"context batch {ctx.B} != latent batch {B}")
+
+        # --- tokens: patchify + register tokens (model.py:533-535)
+        xin = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        xs = self._buf("x", (T, d), dev)
+        ops.patch_embed(xin.contiguous(), self.patch_embed.patch_proj.weight, self.patch_embed.patch_proj.bias,
+                        self.register_tokens, p, out=xs)
+        cos, sin = self._rope(hp, wp, dev)
+        cu_x = self._ws.get(("cu_x", B, L))
+        if cu_x is None or cu_x.device != dev:
+            cu_x = (torch.arange(0, B + 1, dtype=torch.int32) * L).to(dev)
+            self._ws[("cu_x", B, L)] = cu_x
+
+        # --- timestep path (model.py:551-556,578): sinusoid -> MLP -> SiLU -> adaLN / final modulation
+        if self._freqs is None or self._freqs.device != dev:
+            half = d // 2
+            self._freqs = torch.exp(
+                -math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(dev)
+        if timesteps.dtype == torch.bfloat16:
+            t32, tflag = timesteps.float(), 1
+        elif timesteps.dtype == torch.float32:
+            t32, tflag = timesteps, 0
+        else:  # any other dtype: do `timesteps * 1000` in the caller's dtype like model.py:551
+            t32, tflag = (timesteps * 1000).float(), 2
+        temb = ops.timestep_embed(t32.to(dev).contiguous(), tflag, self._freqs, d)
+        te0, te2 = self.time_embed[0], self.time_embed[2]
+        h1 = ops.gemm(temb, te0.weight, te0.bias, act=1, variant=v)
+        st = ops.gemm(h1, te2.weight, te2.bias, act=1, variant=v)           # silu(t_emb)
+        ada = self.adaLN_modulation[1]
+        mod = ops.gemm(st, ada.weight, ada.bias, variant=v)                  # [B, 9d]
+        fm = self.final_modulation[1]
+        fmod = ops.gemm(st, fm.weight, fm.bias, variant=v)                   # [B, 2d]
+        (shift_sa, scale_sa, gate_sa, shift_ca, scale_ca, gate_ca, shift_mlp, scale_mlp, gate_mlp) = (
+            mod[:, k * d:(k + 1) * d] for k in range(9))
+
+        nbuf = self._buf("n", (T, d), dev)
+        qkv = self._buf("qkv", (T, 3 * d), dev)
+        abuf = self._buf("attn", (T, d), dev)
+        qc = self._buf("qc", (T, d), dev)
+        inter = self.blocks[0].mlp.gate_proj.weight.shape[0] if len(self.blocks) else 0
+        hmid = self._buf("hmid", (T, inter), dev)
+        scale = (d // nh) ** -0.5
+
+        for i, blk in enumerate(self.blocks):
+            # ---- self-attention (model.py:283-289)
+            ops.rmsnorm_modulate(xs, blk.norm1.weight, 1, scale_sa, shift_sa, rows_per_sample=L, out=nbuf)
+            sa = blk.self_attn
+            ops.gemm(nbuf, sa.qkv.weight, sa.qkv.bias, epilogue=EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin,
+                     qk_cols=2 * d, rows_per_sample=L, variant=v, out=qkv)
+            ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu_x, cu_x, nh, L, scale, out=abuf)
+            ops.gemm(abuf, sa.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_sa,
+                     rows_per_sample=L, variant=v, out=xs)
+            # ---- cross-attention (model.py:291-297)
+            if blk.cross_attn is not None:
+                ca = blk.cross_attn
+                ops.rmsnorm_modulate(xs, blk.norm2.weight, 1, scale_ca, shift_ca, rows_per_sample=L, out=nbuf)
+                ops.gemm(nbuf, ca.q.weight, ca.q.bias, epilogue=EPI_QKV_ROPE, qk_cols=d, rows_per_sample=L,
+                         variant=v, out=qc)
+                kv = ctx.kvs[i]
+                ops.attention_varlen(qc, kv[:, :d], kv[:, d:], cu_x, ctx.cu_k, nh, L, scale, out=abuf)
+                ops.gemm(abuf, ca.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_ca,
+                         rows_per_sample=L, variant=v, out=xs)
+            # ---- SwiGLU MLP (model.py:299-301)
+            ops.rmsnorm_modulate(xs, blk.norm3.weight, 1, scale_mlp, shift_mlp, rows_per_sample=L, out=nbuf)
+            ops.gemm(nbuf, self._gate_up(i, blk), None, epilogue=EPI_SWIGLU, variant=v, out=hmid)
+            ops.gemm(hmid, blk.mlp.down_proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_mlp,
+                     rows_per_sample=L, variant=v, out=xs)
+
+        # ---- final head (model.py:577-590)
+        fshift, fscale = fmod[:, :d], fmod[:, d:]
+        fw = self.final_norm.weight
+        ops.rmsnorm_modulate(xs, fw, 2 if fw is not None else 0, fscale, fshift, rows_per_sample=L, out=nbuf)
+        o = ops.gemm(nbuf, self.final_proj.weight, self.final_proj.bias, variant=v)
+        out = ops.unpatchify(o, B, C, H, W, p, N_REGISTER)
+        return out if x.dtype == torch.bfloat16 else out.to(x.dtype)

@@ -14,6 +14,12 @@ from ._lib import (EPI_GATED_RES, EPI_QKV_ROPE, EPI_STORE, EPI_SWIGLU, GEMM_AUTO
 
 BF16 = torch.bfloat16
 
+# number of libflite_b200 kernel launches issued through this module (bench.py reports it as gpu_launches)
+LAUNCHES = [0]
+# optional hook called as PROFILE_HOOK(name, phase) with phase "begin"/"end" around selected ops (bench.py
+# uses it to bracket the dominant GEMM with CUDA events on the launching stream)
+PROFILE_HOOK = None
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -48,6 +54,7 @@ def cfg_euler(acc: torch.Tensor, v_uncond: Optional[torch.Tensor], v_cond: torch
     _lib.check(lib.flite_cfg_euler(acc.data_ptr(), int(acc.dtype == torch.float32), _ptr(v_uncond) if do_cfg else None,
                                    v_cond.data_ptr(), float(guidance), float(dt), int(do_cfg), lat_out.data_ptr(),
                                    acc.numel(), _stream()), "cfg_euler")
+    LAUNCHES[0] += 1
 
 
 def rmsnorm_modulate(x: torch.Tensor, weight: Optional[torch.Tensor], weight_mode: int,
@@ -69,6 +76,7 @@ def rmsnorm_modulate(x: torch.Tensor, weight: Optional[torch.Tensor], weight_mod
     _lib.check(lib.flite_rmsnorm_modulate(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), _ptr(weight),
                                           weight_mode, _ptr(scale), _ptr(shift), ld_mod, rows_per_sample, rows, d,
                                           eps, _stream()), "rmsnorm_modulate")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -81,6 +89,7 @@ def rope_qknorm_(buf: torch.Tensor, n_slots: int, cos: Optional[torch.Tensor], s
         _chk(sin, "sin", torch.float32)
     _lib.check(lib.flite_rope_qknorm(buf.data_ptr(), buf.stride(0), buf.shape[0], n_slots, _ptr(cos), _ptr(sin),
                                      rows_per_sample, eps, _stream()), "rope_qknorm")
+    LAUNCHES[0] += 1
 
 
 def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, reg_tokens: torch.Tensor, patch: int,
@@ -98,6 +107,7 @@ def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, reg_t
         out = torch.empty((rows, d), dtype=BF16, device=x.device)
     _lib.check(lib.flite_patch_embed(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), reg_tokens.data_ptr(),
                                      out.data_ptr(), B, C, H, W, patch, d, n_reg, _stream()), "patch_embed")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -111,6 +121,7 @@ def timestep_embed(t_f32: torch.Tensor, t_is_bf16: bool, freqs: torch.Tensor, d:
         out = torch.empty((B, d), dtype=BF16, device=t_f32.device)
     _lib.check(lib.flite_timestep_embed(t_f32.data_ptr(), int(t_is_bf16), freqs.data_ptr(), out.data_ptr(), B, d,
                                         _stream()), "timestep_embed")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -122,6 +133,7 @@ def unpatchify(tok: torch.Tensor, B: int, C: int, H: int, W: int, patch: int, n_
         out = torch.empty((B, C, H, W), dtype=BF16, device=tok.device)
     _lib.check(lib.flite_unpatchify(tok.data_ptr(), tok.stride(0), out.data_ptr(), B, C, H, W, patch, n_reg,
                                     _stream()), "unpatchify")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -139,6 +151,7 @@ def pack_context(src: torch.Tensor, mask_f32: torch.Tensor):
     _lib.check(lib.flite_pack_context(src2.data_ptr(), src2.stride(0), dst.data_ptr(), dst.stride(0),
                                       mask_f32.contiguous().data_ptr(), B, Lc, d, pos.data_ptr(), seqlens.data_ptr(),
                                       cu.data_ptr(), _stream()), "pack_context")
+    LAUNCHES[0] += 3
     return dst, cu
 
 
@@ -162,11 +175,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     for t, n in ((rope_cos, "rope_cos"), (rope_sin, "rope_sin")):
         if t is not None:
             _chk(t, n, torch.float32)
+    hook = PROFILE_HOOK
+    if hook is not None:
+        hook("gemm", "begin", (M, N, K, epilogue))
     _lib.check(lib.flite_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                    out.stride(0), M, N, K, _ptr(bias), act, epilogue, _ptr(resid),
                                    resid.stride(0) if resid is not None else 0, _ptr(gate),
                                    gate.stride(0) if gate is not None else 0, rows_per_sample, _ptr(rope_cos),
                                    _ptr(rope_sin), qk_cols, eps, variant, _stream()), "gemm_bf16")
+    LAUNCHES[0] += 1
+    if hook is not None:
+        hook("gemm", "end", (M, N, K, epilogue))
     return out
 
 
@@ -186,6 +205,7 @@ def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: to
                                           v.data_ptr(), v.stride(0), 0, out.data_ptr(), out.stride(0),
                                           cu_q.data_ptr(), cu_k.data_ptr(), B, num_heads, max_q,
                                           float(softmax_scale), _stream()), "attention_varlen")
+    LAUNCHES[0] += 1
     return out
 
 

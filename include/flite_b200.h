@@ -75,7 +75,9 @@ int flite_rope_qknorm(void* buf, int64_t ld, int rows, int n_slots, const float*
 int flite_patch_embed(const void* x, const void* w, const void* bias, const void* reg_tokens, void* out,
                       int B, int C, int H, int W, int P, int d, int n_reg, void* stream);
 
-/* Sinusoidal timestep embedding; t is fp32 on device, t_is_bf16 reproduces `timesteps*1000` in bf16.  model.py:20-28,551 */
+/* Sinusoidal timestep embedding; t is fp32 on device.                                    model.py:20-28,551
+ *   t_is_bf16: 0 = fp32 timesteps; 1 = bf16 timesteps (reproduces `timesteps*1000` rounded to bf16);
+ *              2 = t already holds float(timesteps*1000) computed in the caller's dtype */
 int flite_timestep_embed(const float* t, int t_is_bf16, const float* freqs, void* out, int B, int d,
                          void* stream);
 

@@ -1,0 +1,137 @@
+"""CPU: the C-ABI library loads and exports every declared symbol; host-side mirrors of the reference API."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import flite_b200
+from flite_b200 import _lib, ops, pipeline
+from oracle import sampler_oracle, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "flite_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(flite_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 13
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/flite_b200.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert _lib.load().flite_abi_version() == 1
+
+
+def test_sass_is_blackwell_native():
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None and not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass     # tcgen05.mma / TMA / tcgen05.ld
+    assert "UTCHMMA.2CTA" in sass                                          # cta_group::2 pair
+    assert "HMMA.16" not in sass                                           # no legacy mma.sync path
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
+def test_fails_loudly_without_gpu():
+    lib = _lib.load()
+    assert lib.flite_check_device() != 0
+    assert lib.flite_last_error()
+    m = flite_b200.DiT(**dict(synth.TINY, depth=1))
+    with pytest.raises(flite_b200.FliteError):
+        m(torch.zeros(1, 16, 32, 32), torch.zeros(1, 8, 4096), torch.ones(1, 8), torch.ones(1))
+    with pytest.raises(flite_b200.FliteError):   # legacy 3-argument call form is routed the same way
+        m(torch.zeros(1, 16, 32, 32), torch.zeros(1, 8, 4096), torch.ones(1))
+    with pytest.raises(_lib.FliteError):
+        ops.cfg_euler(torch.zeros(8), torch.zeros(8), torch.zeros(8), 6.0, 0.1, torch.zeros(8))
+
+
+def test_bad_arguments_return_error_codes():
+    lib = _lib.load()
+    assert lib.flite_gemm_bf16(None, 8, None, 8, None, 8, 1, 64, 64, None, 0, 0, None, 0, None, 0, 0, None, None, 0,
+                               1e-6, 0, None) == -1
+    assert b"null" in lib.flite_last_error()
+    one = ctypes.c_void_p(16)
+    assert lib.flite_gemm_bf16(one, 8, one, 8, one, 8, 1, 64, 63, None, 0, 0, None, 0, None, 0, 0, None, None, 0,
+                               1e-6, 0, None) == -1
+    assert b"K = 63" in lib.flite_last_error()
+    assert lib.flite_cfg_euler(one, 0, one, one, 6.0, 0.1, 1, one, 12, None) == -1
+
+
+@pytest.mark.parametrize("cfg", [synth.TINY, dict(synth.TINY, depth=9, train_bias_and_rms=False)])
+def test_state_dict_layout_matches_reference(cfg):
+    m = flite_b200.DiT(**cfg)
+    sd = m.state_dict()
+    want = synth.param_shapes(cfg)         # key list pinned against the real reference in make_golden
+    assert set(sd) == set(want)
+    for k, shp in want.items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+    for k in ("patch_size", "hidden_size", "use_rope", "gradient_checkpoint", "depth"):
+        assert getattr(m.config, k) == cfg[k]
+    # cross-attention placement: idx % 4 == 0 or idx < 8 (model.py:464)
+    have = [i for i, b in enumerate(m.blocks) if b.cross_attn is not None]
+    assert have == synth.cross_attn_blocks(cfg["depth"])
+    # the reference zero-inits these (model.py:455-456,476-479)
+    assert m.adaLN_modulation[1].weight.abs().sum() == 0 and m.final_proj.weight.abs().sum() == 0
+
+
+def test_reference_state_dict_keys_are_what_the_reference_module_has():
+    ref_model = "/root/reference/f_lite/model.py"
+    if not os.path.exists(ref_model):
+        pytest.skip("reference tree not mounted (GPU box)")
+    from oracle import ref_shim
+    cfg = dict(synth.TINY, depth=2)
+    ref = ref_shim.build_reference_dit(cfg, synth.make_state_dict(cfg))
+    mine = flite_b200.DiT(**cfg)
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    mine.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_schedule_matches_reference_loop():
+    for n, (h, w) in ((4, (32, 32)), (30, (128, 128)), (30, (112, 168))):
+        a = pipeline.default_alpha(h, w)
+        assert a == sampler_oracle.default_alpha(h, w)
+        assert pipeline.time_shift_schedule(n, a) == sampler_oracle.schedule(n, a)
+
+
+def test_interleave_gate_up_layout():
+    inter, d = 256, 8
+    g = torch.arange(inter * d, dtype=torch.float32).view(inter, d)
+    u = -g
+    w = ops.interleave_gate_up(g, u)
+    assert w.shape == (2 * inter, d)
+    for n in range(2 * inter):
+        grp, off = divmod(n, 128)
+        src = g if off < 64 else u
+        assert torch.equal(w[n], src[grp * 64 + off % 64])
+
+
+def test_rope_table_matches_oracle():
+    from flite_b200.model import _rope_table
+    from oracle.dit_oracle import rope_tables
+    cos, sin = _rope_table(256, 6, 10, 10000, 16, round_bf16=True)
+    oc, os_ = rope_tables(256, 6, 10, 10000, "cpu", torch.bfloat16)
+    assert torch.equal(cos, oc[0].float()) and torch.equal(sin, os_[0].float())
+    assert torch.all(cos[:16] == 1) and torch.all(sin[:16] == 0)
+
+
+def test_pipeline_signature_matches_reference():
+    import inspect
+    sig = inspect.signature(pipeline.FLitePipeline.__call__)
+    want = ["self", "prompt", "height", "width", "num_inference_steps", "guidance_scale", "negative_prompt",
+            "num_images_per_prompt", "generator", "dtype", "alpha", "apg_config", "kwargs"]
+    assert list(sig.parameters) == want           # f_lite/pipeline.py:188-202
+    p = sig.parameters
+    assert (p["height"].default, p["width"].default, p["num_inference_steps"].default,
+            p["guidance_scale"].default) == (1024, 1024, 30, 6.0)
+    fsig = inspect.signature(flite_b200.DiT.forward)
+    assert list(fsig.parameters)[:5] == ["self", "x", "context", "context_attn_mask", "timesteps"]  # model.py:526
