@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libflite_b200.so")
 FLITE_OK = 0
 EPI_STORE, EPI_GATED_RES, EPI_SWIGLU, EPI_QKV_ROPE = 0, 1, 2, 3
 GEMM_AUTO, GEMM_1CTA_N256, GEMM_2CTA_N256, GEMM_1CTA_N128, GEMM_1CTA_N64 = 0, 1, 2, 3, 4
+ATTN_AUTO, ATTN_1WG, ATTN_2WG = 0, 1, 2
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 
@@ -32,7 +33,7 @@ SIGNATURES = {
     "flite_pack_context": [_P, _L, _P, _L, _P, _I, _I, _I, _P, _P, _P, _P],
     "flite_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _I, _I, _P, _L, _P, _L, _I, _P, _P, _I, _F,
                         _I, _P],
-    "flite_attention_varlen": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _I, _F, _P],
+    "flite_attention_varlen": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _I, _F, _I, _P],
 }
 
 _lib = None

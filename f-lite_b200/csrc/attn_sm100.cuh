@@ -9,10 +9,12 @@
 //   warp 0     : TMA producer  (Q once, then K_j / V_j tiles of 128 keys, 128B-swizzled)
 //   warp 1     : tcgen05.mma issuer:  S_j = Q K_j^T  (128x128, fp32 in TMEM, double-buffered)
 //                                      O  += P_j V_j  (128x256, fp32 in TMEM; V consumed MN-major)
-//   warps 2..5 : softmax, one query row per thread: running max / sum in registers, lazy O rescale
-//                (only when the row max grows by > 2^8), P_j written as bf16 into swizzled smem,
+//   warps 2..  : softmax warpgroups (kWG = 1 or 2), one query row per thread; with kWG = 2 the two
+//                warpgroups split the 128 key columns of every S tile (and the 256 O columns) in halves and
+//                exchange the partial row maxima through smem.  Running max / sum in registers, lazy O
+//                rescale (only when the row max grows by > 2^8), P_j written as bf16 into swizzled smem,
 //                final O / l -> bf16 -> global.
-// TMEM: S0 [0,128) | S1 [128,256) | O [256,512).   SMEM: Q 64K | K 64K | V 64K | P 32K.
+// TMEM: S0 [0,128) | S1 [128,256) | O [256,512).   SMEM: Q 64K | K 64K | V 64K | P 32K | barriers | exchange.
 #pragma once
 
 #include "common.cuh"
@@ -28,9 +30,14 @@ struct AttnParams {
     float scale_log2;       // softmax_scale * log2(e)
 };
 
-constexpr int ATT_THREADS = 192;
 constexpr int ATT_SQ = 0, ATT_SK = 65536, ATT_SV = 131072, ATT_SP = 196608, ATT_BAR = 229376;
-constexpr int ATT_SMEM = ATT_BAR + 256 + 1024;
+constexpr int ATT_XCH = ATT_BAR + 128;          // float [2 parity][2 half][128 rows]
+constexpr int ATT_SMEM_USED = ATT_XCH + 2048;
+constexpr int ATT_SMEM = 232448;                // 227 KB: everything the SM gives one CTA
+
+FLITE_DEVICE void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 FLITE_DEVICE float fast_exp2(float x) {
     float y;
@@ -38,7 +45,8 @@ FLITE_DEVICE float fast_exp2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int kWG>
+__global__ void __launch_bounds__(64 + 128 * kWG, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
     const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
@@ -49,7 +57,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    if ((smem - smem_raw) + ATT_SMEM_USED > ATT_SMEM) {   // dynamic smem base not aligned as expected
+        if (threadIdx.x == 0) atomicCAS(&g_flite_abort, 0u, (99u << 16) | 0x80000000u);
+        return;
+    }
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_BAR);
+    float* xch = reinterpret_cast<float*>(smem + ATT_XCH);
     uint64_t* q_full = bars + 0;
     uint64_t* k_full = bars + 1;
     uint64_t* k_empty = bars + 2;
@@ -75,7 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             mbar_init(v_empty, 1);
             mbar_init(&s_full[0], 1);
             mbar_init(&s_full[1], 1);
-            mbar_init(p_full, 128);
+            mbar_init(p_full, 128 * kWG);
             mbar_init(pv_done, 1);
             fence_barrier_init();
         }
@@ -152,7 +165,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         __syncwarp();
     } else {
         // ================================ softmax / correction / epilogue ================================
-        const int q = warp_idx & 3;
+        constexpr int NC = 128 / kWG;                        // S columns (keys) per thread per tile
+        constexpr int OC = 256 / kWG;                        // O columns per thread
+        const int q = warp_idx & 3;                          // TMEM lane quarter of this warp
+        const int half = (kWG == 2) ? ((warp_idx - 2) >> 2) : 0;
         const int lane = (int)lane_id();
         const int r = q * 32 + lane;                         // row inside the 128-query tile
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -160,18 +176,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(&s_full[j & 1], (j >> 1) & 1, 17);
             tc_fence_after();
-            const uint32_t ts = tmem_base + lane_off + (j & 1) * 128;
-            const int kv_valid = min(128, k_len - j * 128);
-            // pass 1: row max of the raw scores
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t s[32];
-                tmem_ld_x32(ts + c * 32, s);
-                tmem_ld_wait();
+            const uint32_t ts = tmem_base + lane_off + (j & 1) * 128 + half * NC;
+            const int kv_valid = min(128, k_len - j * 128) - half * NC;   // valid columns of this thread's slice
+            const bool full = kv_valid >= NC;
+            uint32_t s[NC];
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(s[i]));
+            for (int c = 0; c < NC / 32; ++c) tmem_ld_x32(ts + c * 32, s + c * 32);
+            tmem_ld_wait();
+            float mx = -INFINITY;
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < NC; ++i)
+                    if (i < kv_valid) mx = fmaxf(mx, __uint_as_float(s[i]));
+            }
+            if constexpr (kWG == 2) {
+                float* slot = xch + (j & 1) * 256;
+                slot[half * 128 + r] = mx;
+                named_bar_sync(1 + q, 64);
+                mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
             }
             const float m_new = fmaxf(m_used, mx * p.scale_log2);
             const bool need = (j > 0) && (m_new - m_used > 8.0f);
@@ -183,44 +208,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 corr = fast_exp2(m_used - m_new);
                 m_used = m_new;
             }
-            // pass 2: p = 2^(s*scale - m), packed to bf16
-            uint32_t pk[64];
-            float rs = 0.f;
+            // p = 2^(s*scale - m), packed to bf16 in place
+            uint32_t pk[NC / 2];
+            float rs0 = 0.f, rs1 = 0.f;
+            const float neg_m = -m_used;
+            if (full) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t s[32];
-                tmem_ld_x32(ts + c * 32, s);
-                tmem_ld_wait();
+                for (int i = 0; i < NC; i += 2) {
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m));
+                    rs0 += p0; rs1 += p1;
+                    pk[i >> 1] = pack_bf16x2(p0, p1);
+                }
+            } else {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = (c * 32 + i < kv_valid) ? fast_exp2(__uint_as_float(s[i]) * p.scale_log2 - m_used) : 0.f;
-                    float p1 = (c * 32 + i + 1 < kv_valid) ? fast_exp2(__uint_as_float(s[i + 1]) * p.scale_log2 - m_used) : 0.f;
-                    rs += p0 + p1;
-                    pk[c * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+                for (int i = 0; i < NC; i += 2) {
+                    const float p0 = (i < kv_valid) ? fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m)) : 0.f;
+                    const float p1 = (i + 1 < kv_valid) ? fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m)) : 0.f;
+                    rs0 += p0; rs1 += p1;
+                    pk[i >> 1] = pack_bf16x2(p0, p1);
                 }
             }
-            l = l * corr + rs;
+            l = l * corr + (rs0 + rs1);
             // P_{j-1} V_{j-1} must be complete before P (smem) or O (TMEM) are touched
             if (j > 0) {
                 mbar_wait(pv_done, (j - 1) & 1, 18);
                 tc_fence_after();
                 if (need_any) {
 #pragma unroll 1
-                    for (int c = 0; c < 8; ++c) {
+                    for (int c = 0; c < OC / 32; ++c) {
                         uint32_t o[32];
-                        tmem_ld_x32(tmem_o + lane_off + c * 32, o);
+                        tmem_ld_x32(tmem_o + lane_off + half * OC + c * 32, o);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-                        tmem_st_x32(tmem_o + lane_off + c * 32, o);
+                        tmem_st_x32(tmem_o + lane_off + half * OC + c * 32, o);
                     }
                     tmem_st_wait();
                 }
             }
-            // write P (bf16, K-major, 128B swizzle): two 64-key chunks of [128 rows x 128 B]
-            uint8_t* sp_row = smem + ATT_SP + r * 128;
+            // write P (bf16, K-major, 128B swizzle): 64-key chunks of [128 rows x 128 B]
+            uint8_t* sp_row = smem + ATT_SP + r * 128 + ((kWG == 2) ? half * 16384 : 0);
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
+            for (int u = 0; u < NC / 8; ++u) {
                 const int chunk = u >> 3, unit = u & 7;
                 uint4 v = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
                 *reinterpret_cast<uint4*>(sp_row + chunk * 16384 + ((unit ^ (r & 7)) << 4)) = v;
@@ -232,15 +262,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // ---- epilogue: O / l -> bf16 -> out[row, h*256 + c] ----
         const int row_in_seq = qt * 128 + r;
         const bool row_ok = row_in_seq < q_len;
-        __nv_bfloat16* orow = p.out + (long long)(q_beg + row_in_seq) * p.ldo + h * 256;
+        __nv_bfloat16* orow = p.out + (long long)(q_beg + row_in_seq) * p.ldo + h * 256 + half * OC;
         if (n_tiles > 0) {
+            if constexpr (kWG == 2) {
+                // the parity slot of the (non-existent) next tile is free: tile n-2's reads all precede barrier n-1
+                float* slot = xch + (n_tiles & 1) * 256;
+                slot[half * 128 + r] = l;
+                named_bar_sync(1 + q, 64);
+                l += slot[(half ^ 1) * 128 + r];
+            }
             mbar_wait(pv_done, (n_tiles - 1) & 1, 19);
             tc_fence_after();
             const float inv_l = 1.0f / l;
 #pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < OC / 32; ++c) {
                 uint32_t o[32];
-                tmem_ld_x32(tmem_o + lane_off + c * 32, o);
+                tmem_ld_x32(tmem_o + lane_off + half * OC + c * 32, o);
                 tmem_ld_wait();
                 if (row_ok) {
                     uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
@@ -257,7 +294,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             // empty key sequence: flash-attn returns zeros
             uint4* dst = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dst[i] = make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < OC / 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
         }
     }
 

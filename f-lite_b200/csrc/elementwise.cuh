@@ -76,6 +76,66 @@ rmsnorm_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv
     }
 }
 
+// Register-resident variant for d <= 8 * 32 * MAXC: the whole row is loaded once (MAXC independent 16-byte
+// loads in flight per lane), reduced, normalised and written -- one HBM read + one write per element.
+template <int MAXC>
+__global__ void __launch_bounds__(256, (MAXC <= 12) ? 2 : 1)
+rmsnorm_modulate_reg_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
+                            long long ldy, const __nv_bfloat16* __restrict__ w, int weight_mode,
+                            const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift,
+                            long long ld_mod, int rows_per_sample, int rows, int d, float eps) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+    const int nchunk = d >> 3;
+    uint4 v[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = (c < nchunk) ? __ldg(xr + c) : make_uint4(0, 0, 0, 0);
+    }
+    float ssq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        float f[8];
+        unpack8(v[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ssq += f[j] * f[j];
+    }
+    ssq = warp_sum(ssq);
+    const float rstd = rsqrtf(ssq / (float)d + eps);
+    const bool mod = scale != nullptr;
+    const long long s = (long long)(row / rows_per_sample) * ld_mod;
+    uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+            float f[8], wv[8], sc[8], sh[8];
+            unpack8(v[i], f);
+            if (weight_mode != 0) unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), wv);
+            if (mod) {
+                unpack8(__ldg(reinterpret_cast<const uint4*>(scale + s) + c), sc);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(shift + s) + c), sh);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float n;
+                if (weight_mode == 1) n = bf16_round(bf16_round(f[j] * rstd) * wv[j]);
+                else if (weight_mode == 2) n = bf16_round(f[j] * rstd * wv[j]);
+                else n = bf16_round(f[j] * rstd);
+                if (mod) {
+                    n = bf16_round(n * bf16_round(1.0f + sc[j]));
+                    n = n + sh[j];
+                }
+                f[j] = n;
+            }
+            yr[c] = pack8(f);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Standalone RoPE + QK-RMSNorm, in place on packed projections [T, ld] (head_dim 256).
 // One warp per (token, head-slot); slots [0, n_rope_norm) are rotated + normalised, e.g. q and k heads
@@ -84,8 +144,8 @@ rmsnorm_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 rope_qknorm_kernel(__nv_bfloat16* __restrict__ buf, long long ld, int rows, int n_slots,
-                   const float* __restrict__ cos_t, const float* __restrict__ sin_t, int rows_per_sample,
-                   float eps) {
+                   const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t,
+                   int rows_per_sample, float eps) {
     const long long w = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (w >= (long long)rows * n_slots) return;
     const int row = (int)(w / n_slots), slot = (int)(w % n_slots);
@@ -98,9 +158,10 @@ rope_qknorm_kernel(__nv_bfloat16* __restrict__ buf, long long ld, int rows, int 
     float x2[4] = {bf16_lo(b.x), bf16_hi(b.x), bf16_lo(b.y), bf16_hi(b.y)};
     if (cos_t != nullptr) {
         const int pos = row % rows_per_sample;
-        const float4 cv = *reinterpret_cast<const float4*>(cos_t + (long long)pos * 128 + 4 * lane);
-        const float4 sv = *reinterpret_cast<const float4*>(sin_t + (long long)pos * 128 + 4 * lane);
-        const float cs[4] = {cv.x, cv.y, cv.z, cv.w}, sn[4] = {sv.x, sv.y, sv.z, sv.w};
+        const uint2 cv = *reinterpret_cast<const uint2*>(cos_t + (long long)pos * 128 + 4 * lane);
+        const uint2 sv = *reinterpret_cast<const uint2*>(sin_t + (long long)pos * 128 + 4 * lane);
+        const float cs[4] = {bf16_lo(cv.x), bf16_hi(cv.x), bf16_lo(cv.y), bf16_hi(cv.y)};
+        const float sn[4] = {bf16_lo(sv.x), bf16_hi(sv.x), bf16_lo(sv.y), bf16_hi(sv.y)};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float y1 = bf16_round(x1[j] * cs[j] + x2[j] * sn[j]);

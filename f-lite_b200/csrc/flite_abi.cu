@@ -218,14 +218,20 @@ int flite_rmsnorm_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, con
     if ((scale == nullptr) != (shift == nullptr)) return fail(FLITE_ERR_INVALID, "rmsnorm: scale and shift go together");
     if (rows <= 0) return 0;
     if (rows_per_sample <= 0) rows_per_sample = rows;
-    rmsnorm_modulate_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const __nv_bfloat16*)w, weight_mode,
-        (const __nv_bfloat16*)scale, (const __nv_bfloat16*)shift, ld_mod, rows_per_sample, rows, d, eps);
+    auto launch = [&](auto kern, int rows_per_block, int threads) {
+        kern<<<(rows + rows_per_block - 1) / rows_per_block, threads, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const __nv_bfloat16*)w, weight_mode,
+            (const __nv_bfloat16*)scale, (const __nv_bfloat16*)shift, ld_mod, rows_per_sample, rows, d, eps);
+    };
+    if (d <= 8 * 32 * 4) launch(rmsnorm_modulate_reg_kernel<4>, 8, 256);
+    else if (d <= 8 * 32 * 12) launch(rmsnorm_modulate_reg_kernel<12>, 8, 256);
+    else if (d <= 8 * 32 * 16) launch(rmsnorm_modulate_reg_kernel<16>, 8, 256);
+    else launch(rmsnorm_modulate_kernel, 4, 128);
     LAUNCH_CHECK();
     return 0;
 }
 
-int flite_rope_qknorm(void* buf, int64_t ld, int rows, int n_slots, const float* cos_t, const float* sin_t,
+int flite_rope_qknorm(void* buf, int64_t ld, int rows, int n_slots, const void* cos_t, const void* sin_t,
                       int rows_per_sample, float eps, void* stream) {
     if (!buf) return fail(FLITE_ERR_INVALID, "rope_qknorm: null pointer");
     if (ld % 8) return fail(FLITE_ERR_INVALID, "rope_qknorm: ld must be a multiple of 8");
@@ -234,7 +240,8 @@ int flite_rope_qknorm(void* buf, int64_t ld, int rows, int n_slots, const float*
     if (rows_per_sample <= 0) rows_per_sample = rows;
     const long long warps = (long long)rows * n_slots;
     rope_qknorm_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
-        (__nv_bfloat16*)buf, ld, rows, n_slots, cos_t, sin_t, rows_per_sample, eps);
+        (__nv_bfloat16*)buf, ld, rows, n_slots, (const __nv_bfloat16*)cos_t, (const __nv_bfloat16*)sin_t,
+        rows_per_sample, eps);
     LAUNCH_CHECK();
     return 0;
 }
@@ -293,7 +300,7 @@ int flite_pack_context(const void* src, int64_t lds, void* dst, int64_t ldd, con
 
 int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
                     const void* bias, int act, int epilogue, const void* resid, int64_t ldr, const void* gate,
-                    int64_t ld_gate, int rows_per_sample, const float* rope_cos, const float* rope_sin, int qk_cols,
+                    int64_t ld_gate, int rows_per_sample, const void* rope_cos, const void* rope_sin, int qk_cols,
                     float eps, int variant, void* stream) {
     if (!A || !W || !C) return fail(FLITE_ERR_INVALID, "gemm: null pointer");
     if (M <= 0) return 0;
@@ -333,7 +340,7 @@ int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
     p.resid = (const __nv_bfloat16*)resid; p.ldr = ldr;
     p.gate = (const __nv_bfloat16*)gate; p.ld_gate = ld_gate;
     p.rows_per_sample = rows_per_sample;
-    p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.qk_cols = qk_cols; p.eps = eps;
+    p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin; p.qk_cols = qk_cols; p.eps = eps;
 
     CUtensorMap ta, tb;
     int rc = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128);
@@ -353,16 +360,19 @@ int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
 int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
                            int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
                            const int* cu_q, const int* cu_k, int B, int H, int max_q, float softmax_scale,
-                           void* stream) {
+                           int variant, void* stream) {
     if (!q || !k || !v || !out || !cu_q || !cu_k) return fail(FLITE_ERR_INVALID, "attention: null pointer");
     if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || q_col0 % 8 || k_col0 % 8 || v_col0 % 8)
         return fail(FLITE_ERR_INVALID, "attention: strides / column offsets must be multiples of 8");
     if (B <= 0 || H <= 0 || max_q <= 0 || rows_q <= 0) return 0;
     static bool configured = false;
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         configured = true;
     }
+    if (variant != FLITE_ATTN_AUTO && variant != FLITE_ATTN_1WG && variant != FLITE_ATTN_2WG)
+        return fail(FLITE_ERR_INVALID, "attention: unknown variant %d", variant);
     CUtensorMap tq, tk, tv;
     int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)ldq, (uint64_t)ldq, 128);
     if (rc) return rc;
@@ -376,7 +386,8 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     dim3 grid((max_q + 127) / 128, H, B);
-    attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    if (variant == FLITE_ATTN_1WG) attn_fwd_kernel<1><<<grid, 192, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    else attn_fwd_kernel<2><<<grid, 320, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
     LAUNCH_CHECK();
     return 0;
 }

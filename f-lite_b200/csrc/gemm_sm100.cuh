@@ -33,9 +33,9 @@ struct GemmParams {
     const __nv_bfloat16* gate;   // EPI_GATED_RES: gate[(row / rows_per_sample) * ld_gate + col]
     long long ld_gate;
     int rows_per_sample;
-    // EPI_QKV_ROPE: columns are (k in {q,k,v}, head, 256); rope tables [rows_per_sample, 128] fp32
-    const float* rope_cos;
-    const float* rope_sin;
+    // EPI_QKV_ROPE: columns are (k in {q,k,v}, head, 256); rope tables [rows_per_sample, 128] bf16
+    const __nv_bfloat16* rope_cos;
+    const __nv_bfloat16* rope_sin;
     int qk_cols;                 // columns [0, qk_cols) get RoPE (if tables != null) + RMSNorm; rest plain
     float eps;
 };
@@ -276,104 +276,77 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
             } else if constexpr (kEpi == EPI_QKV_ROPE) {
-                // One 256-column tile = one head of q, k or v; one thread = one token row of that head.
+                // One 256-column tile = one head of q, k or v; one thread = one token row of that head, so the
+                // RoPE pairs (j, j+128) and the RMS reduction over the head are thread-local.  The rotated bf16
+                // values of the whole head stay in registers (128 packed words); TMEM is released to the MMA warp
+                // as soon as it has been read, before the normalisation and the stores.
                 static_assert(kEpi != EPI_QKV_ROPE || BLOCK_N == 256, "QKV epilogue needs one head per tile");
                 const bool do_norm = n0 < p.qk_cols;
                 const bool do_rope = do_norm && p.rope_cos != nullptr;
                 const int pos = (row_ok ? row : 0) % p.rows_per_sample;
-                const float4* cosr = reinterpret_cast<const float4*>(p.rope_cos + (long long)pos * 128);
-                const float4* sinr = reinterpret_cast<const float4*>(p.rope_sin + (long long)pos * 128);
+                const uint4* cosr = reinterpret_cast<const uint4*>(p.rope_cos + (long long)pos * 128);
+                const uint4* sinr = reinterpret_cast<const uint4*>(p.rope_sin + (long long)pos * 128);
+                uint32_t keep[128];   // [0,64): columns 0..127, [64,128): columns 128..255 (bf16 pairs)
                 float ssq = 0.f;
-                // pass 1: bias, RoPE (pairs j, j+128), sum of squares of the bf16-rounded rotated values
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t x1[32], x2[32];
-                    tmem_ld_x32(taddr + c * 32, x1);
-                    tmem_ld_x32(taddr + 128 + c * 32, x2);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    uint32_t x1[8], x2[8];
+                    tmem_ld_x8(taddr + c * 8, x1);
+                    tmem_ld_x8(taddr + 128 + c * 8, x2);
                     tmem_ld_wait();
-                    uint32_t o1[16], o2[16];
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const int e0 = c * 32 + hf * 16;  // element offset inside the 128-wide half
-                        float cs[16], sn[16], ba[16], bb[16];
-                        if (do_rope) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float4 cv = __ldg(cosr + (e0 >> 2) + j), sv = __ldg(sinr + (e0 >> 2) + j);
-                                cs[4 * j] = cv.x; cs[4 * j + 1] = cv.y; cs[4 * j + 2] = cv.z; cs[4 * j + 3] = cv.w;
-                                sn[4 * j] = sv.x; sn[4 * j + 1] = sv.y; sn[4 * j + 2] = sv.z; sn[4 * j + 3] = sv.w;
-                            }
-                        }
-                        if (p.bias != nullptr) {
-                            const uint4* b1p = reinterpret_cast<const uint4*>(p.bias + n0 + e0);
-                            const uint4* b2p = reinterpret_cast<const uint4*>(p.bias + n0 + 128 + e0);
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const uint4 v1 = __ldg(b1p + j), v2 = __ldg(b2p + j);
-                                ba[8 * j] = bf16_lo(v1.x); ba[8 * j + 1] = bf16_hi(v1.x); ba[8 * j + 2] = bf16_lo(v1.y);
-                                ba[8 * j + 3] = bf16_hi(v1.y); ba[8 * j + 4] = bf16_lo(v1.z); ba[8 * j + 5] = bf16_hi(v1.z);
-                                ba[8 * j + 6] = bf16_lo(v1.w); ba[8 * j + 7] = bf16_hi(v1.w);
-                                bb[8 * j] = bf16_lo(v2.x); bb[8 * j + 1] = bf16_hi(v2.x); bb[8 * j + 2] = bf16_lo(v2.y);
-                                bb[8 * j + 3] = bf16_hi(v2.y); bb[8 * j + 4] = bf16_lo(v2.z); bb[8 * j + 5] = bf16_hi(v2.z);
-                                bb[8 * j + 6] = bf16_lo(v2.w); bb[8 * j + 7] = bf16_hi(v2.w);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) { ba[j] = 0.f; bb[j] = 0.f; }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const int jj = hf * 16 + j;
-                            float a0 = bf16_round(__uint_as_float(x1[jj]) + ba[j]);
-                            float a1 = bf16_round(__uint_as_float(x1[jj + 1]) + ba[j + 1]);
-                            float b0 = bf16_round(__uint_as_float(x2[jj]) + bb[j]);
-                            float b1 = bf16_round(__uint_as_float(x2[jj + 1]) + bb[j + 1]);
-                            if (do_rope) {
-                                // model.py:412-413: y1 = x1*cos + x2*sin ; y2 = x1*(-sin) + x2*cos (fp32, then cast)
-                                const float y10 = bf16_round(a0 * cs[j] + b0 * sn[j]);
-                                const float y20 = bf16_round(a0 * (-sn[j]) + b0 * cs[j]);
-                                const float y11 = bf16_round(a1 * cs[j + 1] + b1 * sn[j + 1]);
-                                const float y21 = bf16_round(a1 * (-sn[j + 1]) + b1 * cs[j + 1]);
-                                a0 = y10; b0 = y20; a1 = y11; b1 = y21;
-                            }
-                            ssq += a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1;
-                            o1[jj >> 1] = pack_bf16x2(a0, a1);
-                            o2[jj >> 1] = pack_bf16x2(b0, b1);
-                        }
+                    uint4 b1 = make_uint4(0, 0, 0, 0), b2 = b1, cs = b1, sn = b1;
+                    if (p.bias != nullptr) {
+                        b1 = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + c * 8));
+                        b2 = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + 128 + c * 8));
                     }
-                    if (!do_norm && row_ok) {
-                        uint4* cp1 = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + n0 + c * 32);
-                        uint4* cp2 = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + n0 + 128 + c * 32);
+                    if (do_rope) {
+                        cs = __ldg(cosr + c);
+                        sn = __ldg(sinr + c);
+                    }
+                    const uint32_t b1w[4] = {b1.x, b1.y, b1.z, b1.w}, b2w[4] = {b2.x, b2.y, b2.z, b2.w};
+                    const uint32_t csw[4] = {cs.x, cs.y, cs.z, cs.w}, snw[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // reference rounding points: qkv = bf16(acc + bias); rope in fp32 -> bf16; norm in fp32 -> bf16
+                        float a0 = bf16_round(__uint_as_float(x1[2 * j]) + bf16_lo(b1w[j]));
+                        float a1 = bf16_round(__uint_as_float(x1[2 * j + 1]) + bf16_hi(b1w[j]));
+                        float e0 = bf16_round(__uint_as_float(x2[2 * j]) + bf16_lo(b2w[j]));
+                        float e1 = bf16_round(__uint_as_float(x2[2 * j + 1]) + bf16_hi(b2w[j]));
+                        if (do_rope) {
+                            // model.py:412-413: y1 = x1*cos + x2*sin ; y2 = x1*(-sin) + x2*cos
+                            const float cl = bf16_lo(csw[j]), ch = bf16_hi(csw[j]), sl = bf16_lo(snw[j]), sh = bf16_hi(snw[j]);
+                            const float y10 = bf16_round(a0 * cl + e0 * sl), y20 = bf16_round(a0 * (-sl) + e0 * cl);
+                            const float y11 = bf16_round(a1 * ch + e1 * sh), y21 = bf16_round(a1 * (-sh) + e1 * ch);
+                            a0 = y10; e0 = y20; a1 = y11; e1 = y21;
+                        }
+                        ssq += a0 * a0 + a1 * a1 + e0 * e0 + e1 * e1;
+                        keep[c * 4 + j] = pack_bf16x2(a0, a1);
+                        keep[64 + c * 4 + j] = pack_bf16x2(e0, e1);
+                    }
+                }
+                // all TMEM reads of this accumulator are done: hand it back to the MMA warp now
+                tc_fence_before();
+                __syncwarp();
+                if (elect_one()) {
+                    if constexpr (kCtaGroup == 1) mbar_arrive(&tmem_empty_bar[acc]);
+                    else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+                }
+                __syncwarp();
+                if (row_ok) {
+                    const float rstd = do_norm ? rsqrtf(ssq * (1.0f / 256.0f) + p.eps) : 1.0f;
+                    uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + n0);
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) {
+                        uint32_t o[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            cp1[j] = make_uint4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
-                            cp2[j] = make_uint4(o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
+                            const uint32_t v = keep[4 * u + j];
+                            o[j] = do_norm ? pack_bf16x2(bf16_lo(v) * rstd, bf16_hi(v) * rstd) : v;
                         }
-                    } else if (do_norm) {
-                        // park the rotated bf16 pairs back in TMEM (same columns, packed) for pass 2
-                        tmem_st_x16(taddr + c * 32, o1);
-                        tmem_st_x16(taddr + 128 + c * 32, o2);
+                        cp[u] = make_uint4(o[0], o[1], o[2], o[3]);
                     }
                 }
-                if (do_norm) {
-                    tmem_st_wait();
-                    const float rstd = rsqrtf(ssq * (1.0f / 256.0f) + p.eps);
-#pragma unroll 1
-                    for (int c = 0; c < 8; ++c) {
-                        uint32_t v[16];
-                        tmem_ld_x16(taddr + (c >> 2) * 128 + (c & 3) * 32, v);
-                        tmem_ld_wait();
-                        uint32_t o[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(bf16_lo(v[j]) * rstd, bf16_hi(v[j]) * rstd);
-                        if (row_ok) {
-                            uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + n0 + (c >> 2) * 128 +
-                                                                 (c & 3) * 32);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) cp[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                        }
-                    }
-                }
+                continue;   // barrier already signalled
             }
             tc_fence_before();
             __syncwarp();

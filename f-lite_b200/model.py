@@ -108,9 +108,10 @@ class PatchEmbed(nn.Module):
 
 
 def _rope_table(head_dim: int, h: int, w: int, base: float, n_reg: int, round_bf16: bool):
-    """cos/sin [n_reg + h*w, head_dim/2] fp32, values as the reference module holds them
-    (model.py:334-386; the buffers are bf16 after ``model.to(bf16)``).
-    Built with the same CPU torch ops as the reference constructor so the table is bit-identical."""
+    """cos/sin [n_reg + h*w, head_dim/2], values as the reference module holds them (model.py:334-386;
+    the buffers are bf16 after ``model.to(bf16)``).  Built with the same CPU torch
+    ops as the reference constructor so the table is bit-identical; returned in fp32 (``round_bf16`` only
+    rounds the values), the model stores them as bf16 on the device."""
     dim = head_dim // 2
     inv = torch.tensor([1.0 / (base ** (i / dim)) for i in range(0, dim, 2)], dtype=torch.float32)
     fh = torch.outer(torch.arange(h, dtype=torch.float32), inv).unsqueeze(1).repeat(1, w, 1)
@@ -202,7 +203,7 @@ class DiT(nn.Module):
         if key not in self._rope_cache:
             hd = self.config.hidden_size // self.config.num_heads
             cos, sin = _rope_table(hd, h, w, self.config.rope_base, N_REGISTER, round_bf16=True)
-            self._rope_cache[key] = (cos.to(device), sin.to(device))
+            self._rope_cache[key] = (cos.to(device, torch.bfloat16), sin.to(device, torch.bfloat16))
         return self._rope_cache[key]
 
     def _gate_up(self, i, blk):

@@ -85,8 +85,8 @@ def rope_qknorm_(buf: torch.Tensor, n_slots: int, cos: Optional[torch.Tensor], s
     lib = _lib.load()
     _chk(buf, "buf")
     if cos is not None:
-        _chk(cos, "cos", torch.float32)
-        _chk(sin, "sin", torch.float32)
+        _chk(cos, "cos")
+        _chk(sin, "sin")
     _lib.check(lib.flite_rope_qknorm(buf.data_ptr(), buf.stride(0), buf.shape[0], n_slots, _ptr(cos), _ptr(sin),
                                      rows_per_sample, eps, _stream()), "rope_qknorm")
     LAUNCHES[0] += 1
@@ -174,7 +174,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
             _chk(t, n)
     for t, n in ((rope_cos, "rope_cos"), (rope_sin, "rope_sin")):
         if t is not None:
-            _chk(t, n, torch.float32)
+            _chk(t, n)
+            if not t.is_contiguous():
+                raise _lib.FliteError(f"{n} must be contiguous [rows_per_sample, 128]")
     hook = PROFILE_HOOK
     if hook is not None:
         hook("gemm", "begin", (M, N, K, epilogue))
@@ -190,7 +192,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
 
 def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: torch.Tensor, cu_k: torch.Tensor,
-                     num_heads: int, max_q: int, softmax_scale: float, out: Optional[torch.Tensor] = None):
+                     num_heads: int, max_q: int, softmax_scale: float, out: Optional[torch.Tensor] = None,
+                     variant: int = 0):
     """q [Tq, >= H*256] / k, v [Tk, >= H*256] are (possibly strided column) views of projection buffers."""
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
@@ -204,7 +207,7 @@ def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: to
     _lib.check(lib.flite_attention_varlen(q.data_ptr(), q.stride(0), Tq, 0, k.data_ptr(), k.stride(0), k.shape[0], 0,
                                           v.data_ptr(), v.stride(0), 0, out.data_ptr(), out.stride(0),
                                           cu_q.data_ptr(), cu_k.data_ptr(), B, num_heads, max_q,
-                                          float(softmax_scale), _stream()), "attention_varlen")
+                                          float(softmax_scale), variant, _stream()), "attention_varlen")
     LAUNCHES[0] += 1
     return out
 

@@ -44,6 +44,11 @@ extern "C" {
 #define FLITE_GEMM_1CTA_N128 3
 #define FLITE_GEMM_1CTA_N64 4
 
+/* attention kernel variants */
+#define FLITE_ATTN_AUTO 0
+#define FLITE_ATTN_1WG 1   /* one softmax warpgroup (192 threads)                 */
+#define FLITE_ATTN_2WG 2   /* two softmax warpgroups splitting the key columns    */
+
 int flite_abi_version(void);
 const char* flite_last_error(void);
 
@@ -67,8 +72,9 @@ int flite_rmsnorm_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, con
                            int rows, int d, float eps, void* stream);
 
 /* In-place RoPE + QK-RMSNorm on head slots [0, n_slots) of buf[rows, ld] (head_dim 256).  model.py:166-180
- *   cos/sin: fp32 [rows_per_sample, 128] or NULL (no rotation, cross-attention)          model.py:197 */
-int flite_rope_qknorm(void* buf, int64_t ld, int rows, int n_slots, const float* cos_t, const float* sin_t,
+ *   cos/sin: bf16 [rows_per_sample, 128] (the values the reference's bf16 buffers hold) or NULL (no rotation,
+ *   cross-attention, model.py:197) */
+int flite_rope_qknorm(void* buf, int64_t ld, int rows, int n_slots, const void* cos_t, const void* sin_t,
                       int rows_per_sample, float eps, void* stream);
 
 /* Patch embedding + register tokens -> tokens[B*(n_reg + hw), d].                         model.py:318-328,535 */
@@ -96,12 +102,12 @@ int flite_pack_context(const void* src, int64_t lds, void* dst, int64_t ldd, con
  *   bias [N] or NULL; act: 0 none, 1 SiLU (EPI_STORE only)
  *   EPI_GATED_RES: resid [M, ldr], gate row = gate + (row / rows_per_sample) * ld_gate
  *   EPI_SWIGLU   : C has N/2 columns
- *   EPI_QKV_ROPE : columns [0, qk_cols) are 256-wide heads that get RoPE (rope_cos/sin fp32
+ *   EPI_QKV_ROPE : columns [0, qk_cols) are 256-wide heads that get RoPE (rope_cos/sin bf16
  *                  [rows_per_sample, 128], may be NULL) and RMSNorm(eps); the rest is bias only */
 int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N,
                     int K, const void* bias, int act, int epilogue, const void* resid, int64_t ldr,
-                    const void* gate, int64_t ld_gate, int rows_per_sample, const float* rope_cos,
-                    const float* rope_sin, int qk_cols, float eps, int variant, void* stream);
+                    const void* gate, int64_t ld_gate, int rows_per_sample, const void* rope_cos,
+                    const void* rope_sin, int qk_cols, float eps, int variant, void* stream);
 
 /* Varlen non-causal flash attention, head_dim 256.                                        model.py:203-211
  *   q[rows_q, ldq] head h at columns q_col0 + 256 h (same for k, v); cu_q / cu_k int32 [B+1] on device;
@@ -109,7 +115,7 @@ int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
 int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
                            int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out,
                            int64_t ldo, const int* cu_q, const int* cu_k, int B, int H, int max_q,
-                           float softmax_scale, void* stream);
+                           float softmax_scale, int variant, void* stream);
 
 #ifdef __cplusplus
 }

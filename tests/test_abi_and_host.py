@@ -121,6 +121,7 @@ def test_rope_table_matches_oracle():
     cos, sin = _rope_table(256, 6, 10, 10000, 16, round_bf16=True)
     oc, os_ = rope_tables(256, 6, 10, 10000, "cpu", torch.bfloat16)
     assert torch.equal(cos, oc[0].float()) and torch.equal(sin, os_[0].float())
+    assert torch.equal(cos.bfloat16().float(), cos)      # exactly representable: stored as bf16 on the device
     assert torch.all(cos[:16] == 1) and torch.all(sin[:16] == 0)
 
 

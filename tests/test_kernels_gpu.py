@@ -59,7 +59,7 @@ def test_cfg_euler_fp32_accumulator():
 
 
 # ----------------------------------------------------------------------------- norm + modulate
-@pytest.mark.parametrize("rows,d,B", [(2 * 272, 512, 2), (2 * 4112, 3072, 2), (5, 256, 1)])
+@pytest.mark.parametrize("rows,d,B", [(2 * 272, 512, 2), (2 * 4112, 3072, 2), (5, 256, 1), (37, 4096, 1), (9, 4608, 3)])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_rmsnorm_modulate(rows, d, B, mode):
     from flite_b200 import ops
@@ -133,7 +133,7 @@ def _rope_norm_ref(qkv, cos, sin, n_heads_rot, B):
     M = qkv.shape[0]
     x = qkv[:, :n_heads_rot * 256].reshape(M, n_heads_rot, 256).float()
     if cos is not None:
-        c, s = cos.repeat(B, 1)[:, None, :], sin.repeat(B, 1)[:, None, :]
+        c, s = cos.float().repeat(B, 1)[:, None, :], sin.float().repeat(B, 1)[:, None, :]
         x1, x2 = x[..., :128], x[..., 128:]
         x = torch.cat([x1 * c + x2 * s, x1 * (-s) + x2 * c], -1).bfloat16().float()     # model.py:403-414
     y = (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6)).bfloat16()            # model.py:101-108
@@ -148,7 +148,7 @@ def test_gemm_qkv_rope_qknorm_epilogue(variant, with_rope):
     M = B * L
     a, w, b = rnd(M, d, scale=0.5, seed=1), rnd(3 * d, d, scale=0.05, seed=2), rnd(3 * d, seed=3)
     ang = torch.rand(L, 128, device=DEV) * 6.28
-    cos, sin = (ang.cos().bfloat16().float(), ang.sin().bfloat16().float()) if with_rope else (None, None)
+    cos, sin = (ang.cos().bfloat16(), ang.sin().bfloat16()) if with_rope else (None, None)
     out = ops.gemm(a, w, b, epilogue=ops.EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin, qk_cols=2 * d,
                    rows_per_sample=L, variant=variant)
     ref = _rope_norm_ref(F.linear(a, w, b), cos, sin, 2 * d // 256, B)
@@ -164,8 +164,9 @@ ATT_CASES = [(1, 1, 128, 128), (1, 2, 256, 384), (2, 2, 272, 272), (2, 2, 272, 1
              (2, 12, 4112, 256)]
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("B,H,Lq,Lk", ATT_CASES)
-def test_attention_uniform(B, H, Lq, Lk):
+def test_attention_uniform(B, H, Lq, Lk, variant):
     from flite_b200 import ops
     from oracle.dit_oracle import flash_attn_varlen
     d = H * 256
@@ -173,7 +174,7 @@ def test_attention_uniform(B, H, Lq, Lk):
     kv = rnd(B * Lk, 2 * d, seed=2)
     cu_q = torch.arange(B + 1, device=DEV, dtype=torch.int32) * Lq
     cu_k = torch.arange(B + 1, device=DEV, dtype=torch.int32) * Lk
-    out = ops.attention_varlen(q, kv[:, :d], kv[:, d:], cu_q, cu_k, H, Lq, 256 ** -0.5)
+    out = ops.attention_varlen(q, kv[:, :d], kv[:, d:], cu_q, cu_k, H, Lq, 256 ** -0.5, variant=variant)
     ref = flash_attn_varlen(q.view(-1, H, 256), kv[:, :d].reshape(-1, H, 256), kv[:, d:].reshape(-1, H, 256),
                             cu_q, cu_k, 256 ** -0.5)
     assert rel(out, ref.reshape(-1, d)) <= 5e-3          # bf16 output + bf16 P, same as FA2's own error

@@ -101,7 +101,8 @@ def test_sampler_trajectory_vs_reference(golden_dir):
     olat = sampler_oracle.sample_pipeline(fn, x[:b].bfloat16(), ctx[:b].bfloat16(), ctx[b:].bfloat16(),
                                           mask.bfloat16(), g["steps"], g["guidance"], trace=otrace)
     v0 = trace[0][:b] + g["guidance"] * (trace[0][b:] - trace[0][:b])     # my trace holds [uncond; cond]
-    assert rel(v0, otrace[0]) <= 2 * TOL                         # same inputs at step 0 (CFG amplifies x6)
+    gv0 = g["velocities"][0].to(DEV)                             # fp32 reference, CFG-combined (x6 amplification)
+    assert rel(v0, gv0) <= max(1.5 * rel(otrace[0], gv0), 2 * TOL)
     r_final = rel(lat, olat)
     r_gold = rel(lat.cpu(), g["latents_pipeline"])               # fp32 reference trajectory (CPU fixture)
     r_ref_gold = rel(olat.cpu(), g["latents_pipeline"])

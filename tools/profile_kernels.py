@@ -18,7 +18,7 @@ if which in ("gemm", "all"):
     for _ in range(6):
         ops.gemm(out, wdn, None, epilogue=ops.EPI_GATED_RES, resid=x, gate=gate, rows_per_sample=T // 2, out=x)
     wq = (torch.randn(3 * d, d, device=dev) * 0.02).bfloat16(); bq = torch.randn(3 * d, device=dev).bfloat16()
-    cos = torch.rand(T // 2, 128, device=dev); sin = torch.rand(T // 2, 128, device=dev)
+    cos = torch.rand(T // 2, 128, device=dev).bfloat16(); sin = torch.rand(T // 2, 128, device=dev).bfloat16()
     qkv = torch.empty(T, 3 * d, device=dev, dtype=torch.bfloat16)
     for _ in range(6):
         ops.gemm(a, wq, bq, epilogue=ops.EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin, qk_cols=2 * d, rows_per_sample=T // 2, out=qkv)
