@@ -1,0 +1,291 @@
+// 2-CTA (cta_group::2) varlen flash attention forward, head_dim 256, sm_100a.
+//
+// A cluster of two CTAs processes two adjacent 128-query tiles of the same (head, sequence) and shares every
+// K/V tile: with tcgen05.mma.cta_group::2 the pair computes S = Q K^T as a 256 x 128 MMA (each CTA stages only
+// 64 of the 128 key rows) and O += P V as a 256 x 256 MMA (each CTA stages only 128 of the 256 head-dim columns
+// of V), so K/V traffic from L2 per query row is halved relative to attn_fwd_kernel and the freed shared memory
+// double-buffers K and V (loads of tile j+1 overlap the MMAs of tile j).
+//   SMEM / CTA: Q 64K | K half-tile 32K x2 | V half-tile 32K x2 | P 32K | barriers | exchange
+//   TMEM / CTA: S0 [0,128) | S1 [128,256) | O [256,512)   (own 128 query rows)
+// Roles per CTA: warp 0 TMA producer (own halves; complete_tx on the leader's barriers), warp 1 MMA issuer
+// (leader CTA only; commits multicast to both CTAs), warps 2.. softmax warpgroups (as in attn_fwd_kernel).
+#pragma once
+
+#include "attn_sm100.cuh"
+
+namespace flite {
+
+constexpr int ATT2_SQ = 0, ATT2_SK = 65536, ATT2_SV = 131072, ATT2_SP = 196608;
+
+template <int kWG>
+__global__ void __launch_bounds__(64 + 128 * kWG, 1)
+attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+    const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
+    const int q_beg = p.cu_q[b], q_len = p.cu_q[b + 1] - q_beg;
+    if ((qt & ~1) * 128 >= q_len) return;  // uniform for the whole cluster, before any barrier / TMEM allocation
+    const int k_beg = p.cu_k[b], k_len = p.cu_k[b + 1] - k_beg;
+    const int n_tiles = (k_len + 127) / 128;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool is_leader = cta_rank == 0;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const bool smem_bad = (smem - smem_raw) + ATT_SMEM_USED > ATT_SMEM;   // same value in both CTAs
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_BAR);
+    float* xch = reinterpret_cast<float*>(smem + ATT_XCH);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;    // [2]  leader
+    uint64_t* k_empty = bars + 3;   // [2]  each CTA
+    uint64_t* v_full = bars + 5;    // [2]  leader
+    uint64_t* v_empty = bars + 7;   // [2]  each CTA
+    uint64_t* s_full = bars + 9;    // [2]  each CTA
+    uint64_t* p_full = bars + 11;   //      leader, one arrival per softmax warp of both CTAs
+    uint64_t* pv_done = bars + 12;  //      each CTA
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp_idx = threadIdx.x >> 5;
+    if (smem_bad) {
+        if (threadIdx.x == 0) atomicCAS(&g_flite_abort, 0u, (98u << 16) | 0x80000000u);
+        return;
+    }
+    if (warp_idx == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+    }
+    if (warp_idx == 1) {
+        if (elect_one()) {
+            mbar_init(q_full, 1);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&k_full[i], 1);
+                mbar_init(&k_empty[i], 1);
+                mbar_init(&v_full[i], 1);
+                mbar_init(&v_empty[i], 1);
+                mbar_init(&s_full[i], 1);
+            }
+            mbar_init(p_full, 2 * 4 * kWG);
+            mbar_init(pv_done, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<2>(tmem_ptr_smem, 512);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_o = tmem_base + 256;
+
+    const int q_row0 = q_beg + qt * 128;
+
+    if (warp_idx == 0) {
+        // ================================ TMA producer (both CTAs) ================================
+        if (elect_one() && n_tiles > 0) {
+            if (is_leader) mbar_arrive_expect_tx(q_full, 2 * 65536);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                tma_load_2d_cg2(smem + ATT2_SQ + c * 16384, &tmap_q, q_full, 0, p.q_col0 + h * 256 + c * 64, q_row0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int st = j & 1;
+                const uint32_t ph = ((j >> 1) & 1) ^ 1;
+                const int krow = k_beg + j * 128;
+                mbar_wait<true>(&k_empty[st], ph, 21);
+                if (is_leader) mbar_arrive_expect_tx(&k_full[st], 2 * 32768);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)   // this CTA's 64 key rows, 4 chunks of 64 head-dim columns
+                    tma_load_2d_cg2(smem + ATT2_SK + st * 32768 + c * 8192, &tmap_k, &k_full[st], 0,
+                                    p.k_col0 + h * 256 + c * 64, krow + (int)cta_rank * 64);
+                mbar_wait<true>(&v_empty[st], ph, 22);
+                if (is_leader) mbar_arrive_expect_tx(&v_full[st], 2 * 32768);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)   // all 128 key rows, this CTA's 128 head-dim columns
+                    tma_load_2d_cg2(smem + ATT2_SV + st * 32768 + c * 16384, &tmap_v, &v_full[st], 0,
+                                    p.v_col0 + h * 256 + (int)cta_rank * 128 + c * 64, krow);
+            }
+        }
+        __syncwarp();
+    } else if (warp_idx == 1) {
+        // ================================ MMA issuer (leader CTA) ================================
+        if (is_leader && elect_one() && n_tiles > 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(256, 128, 0, 0);   // Q (K-major) x K (K-major)
+            constexpr uint32_t idesc_o = make_idesc_bf16(256, 256, 0, 1);   // P (K-major) x V (MN-major)
+            const uint32_t sq = smem_u32(smem + ATT2_SQ), sk = smem_u32(smem + ATT2_SK);
+            const uint32_t sv = smem_u32(smem + ATT2_SV), sp = smem_u32(smem + ATT2_SP);
+            auto issue_s = [&](int j) {
+                const int st = j & 1;
+                mbar_wait<true>(&k_full[st], (j >> 1) & 1, 23);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (j & 1) * 128;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t offq = (k >> 2) * 16384 + (k & 3) * 32;
+                    const uint32_t offk = st * 32768 + (k >> 2) * 8192 + (k & 3) * 32;
+                    umma_ss<2>(d, make_smem_desc_sw128(sq + offq, 16, 1024), make_smem_desc_sw128(sk + offk, 16, 1024),
+                               idesc_s, k != 0 ? 1u : 0u);
+                }
+                umma_commit_cg2(&k_empty[st], 0x3);
+                umma_commit_cg2(&s_full[j & 1], 0x3);
+            };
+            mbar_wait<true>(q_full, 0, 24);
+            issue_s(0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int st = j & 1;
+                if (j + 1 < n_tiles) issue_s(j + 1);
+                mbar_wait<true>(p_full, j & 1, 25);
+                mbar_wait<true>(&v_full[st], (j >> 1) & 1, 26);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t da = make_smem_desc_sw128(sp + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sv + st * 32768 + k * 2048, 16384, 1024);
+                    umma_ss<2>(tmem_o, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);
+                }
+                umma_commit_cg2(&v_empty[st], 0x3);
+                umma_commit_cg2(pv_done, 0x3);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ softmax / correction / epilogue ================================
+        constexpr int NC = 128 / kWG;                        // S columns (keys) per thread per tile
+        constexpr int OC = 256 / kWG;                        // O columns per thread
+        const int q = warp_idx & 3;                          // TMEM lane quarter of this warp
+        const int half = (kWG == 2) ? ((warp_idx - 2) >> 2) : 0;
+        const int lane = (int)lane_id();
+        const int r = q * 32 + lane;                         // row inside the 128-query tile
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        float m_used = -INFINITY, l = 0.f;
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait<true>(&s_full[j & 1], (j >> 1) & 1, 27);
+            tc_fence_after();
+            const uint32_t ts = tmem_base + lane_off + (j & 1) * 128 + half * NC;
+            const int kv_valid = min(128, k_len - j * 128) - half * NC;   // valid columns of this thread's slice
+            const bool full = kv_valid >= NC;
+            uint32_t s[NC];
+#pragma unroll
+            for (int c = 0; c < NC / 32; ++c) tmem_ld_x32(ts + c * 32, s + c * 32);
+            tmem_ld_wait();
+            float mx = -INFINITY;
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < NC; ++i)
+                    if (i < kv_valid) mx = fmaxf(mx, __uint_as_float(s[i]));
+            }
+            if constexpr (kWG == 2) {
+                float* slot = xch + (j & 1) * 256;
+                slot[half * 128 + r] = mx;
+                named_bar_sync(1 + q, 64);
+                mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
+            }
+            const float m_new = fmaxf(m_used, mx * p.scale_log2);
+            const bool need = (j > 0) && (m_new - m_used > 8.0f);
+            const bool need_any = __any_sync(0xffffffffu, need);
+            float corr = 1.0f;
+            if (j == 0) {
+                m_used = m_new;
+            } else if (need_any) {
+                corr = fast_exp2(m_used - m_new);
+                m_used = m_new;
+            }
+            // p = 2^(s*scale - m), packed to bf16 in place
+            uint32_t pk[NC / 2];
+            float rs0 = 0.f, rs1 = 0.f;
+            const float neg_m = -m_used;
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < NC; i += 2) {
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m));
+                    rs0 += p0; rs1 += p1;
+                    pk[i >> 1] = pack_bf16x2(p0, p1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NC; i += 2) {
+                    const float p0 = (i < kv_valid) ? fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m)) : 0.f;
+                    const float p1 = (i + 1 < kv_valid) ? fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m)) : 0.f;
+                    rs0 += p0; rs1 += p1;
+                    pk[i >> 1] = pack_bf16x2(p0, p1);
+                }
+            }
+            l = l * corr + (rs0 + rs1);
+            // P_{j-1} V_{j-1} must be complete before P (smem) or O (TMEM) are touched
+            if (j > 0) {
+                mbar_wait<true>(pv_done, (j - 1) & 1, 28);
+                tc_fence_after();
+                if (need_any) {
+#pragma unroll 1
+                    for (int c = 0; c < OC / 32; ++c) {
+                        uint32_t o[32];
+                        tmem_ld_x32(tmem_o + lane_off + half * OC + c * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                        tmem_st_x32(tmem_o + lane_off + half * OC + c * 32, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            // write P (bf16, K-major, 128B swizzle): 64-key chunks of [128 rows x 128 B]
+            uint8_t* sp_row = smem + ATT2_SP + r * 128 + ((kWG == 2) ? half * 16384 : 0);
+#pragma unroll
+            for (int u = 0; u < NC / 8; ++u) {
+                const int chunk = u >> 3, unit = u & 7;
+                uint4 v = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                *reinterpret_cast<uint4*>(sp_row + chunk * 16384 + ((unit ^ (r & 7)) << 4)) = v;
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive_cluster(p_full, 0);   // P of both CTAs is consumed by the leader's MMAs
+            __syncwarp();
+        }
+        // ---- epilogue: O / l -> bf16 -> out[row, h*256 + c] ----
+        const int row_in_seq = qt * 128 + r;
+        const bool row_ok = row_in_seq < q_len;
+        __nv_bfloat16* orow = p.out + (long long)(q_beg + row_in_seq) * p.ldo + h * 256 + half * OC;
+        if (n_tiles > 0) {
+            if constexpr (kWG == 2) {
+                // the parity slot of the (non-existent) next tile is free: tile n-2's reads all precede barrier n-1
+                float* slot = xch + (n_tiles & 1) * 256;
+                slot[half * 128 + r] = l;
+                named_bar_sync(1 + q, 64);
+                l += slot[(half ^ 1) * 128 + r];
+            }
+            mbar_wait<true>(pv_done, (n_tiles - 1) & 1, 29);
+            tc_fence_after();
+            const float inv_l = 1.0f / l;
+#pragma unroll 1
+            for (int c = 0; c < OC / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld_x32(tmem_o + lane_off + half * OC + c * 32, o);
+                tmem_ld_wait();
+                if (row_ok) {
+                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        dst[i] = make_uint4(
+                            pack_bf16x2(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
+                }
+            }
+        } else if (row_ok) {
+            // empty key sequence: flash-attn returns zeros
+            uint4* dst = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+            for (int i = 0; i < OC / 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp_idx == 1) tmem_dealloc<2>(tmem_base, 512);
+}
+
+}  // namespace flite

@@ -11,6 +11,7 @@
 #include <unordered_map>
 
 #include "../../include/flite_b200.h"
+#include "attn_cg2_sm100.cuh"
 #include "attn_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
@@ -369,14 +370,18 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_cg2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_cg2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         configured = true;
     }
-    if (variant != FLITE_ATTN_AUTO && variant != FLITE_ATTN_1WG && variant != FLITE_ATTN_2WG)
+    if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_2CTA_2WG)
         return fail(FLITE_ERR_INVALID, "attention: unknown variant %d", variant);
+    if (variant == FLITE_ATTN_AUTO) variant = FLITE_ATTN_2CTA_1WG;
+    const bool cg2 = variant == FLITE_ATTN_2CTA_1WG || variant == FLITE_ATTN_2CTA_2WG;
     CUtensorMap tq, tk, tv;
     int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)ldq, (uint64_t)ldq, 128);
     if (rc) return rc;
-    rc = make_tmap(&tk, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldk, (uint64_t)ldk, 128);
+    rc = make_tmap(&tk, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldk, (uint64_t)ldk, cg2 ? 64 : 128);
     if (rc) return rc;
     rc = make_tmap(&tv, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldv, (uint64_t)ldv, 128);
     if (rc) return rc;
@@ -385,10 +390,28 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
     p.out = (__nv_bfloat16*)out; p.ldo = ldo;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
-    dim3 grid((max_q + 127) / 128, H, B);
-    if (variant == FLITE_ATTN_1WG) attn_fwd_kernel<1><<<grid, 192, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
-    else attn_fwd_kernel<2><<<grid, 320, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
-    LAUNCH_CHECK();
+    const int q_tiles = (max_q + 127) / 128;
+    if (!cg2) {
+        dim3 grid(q_tiles, H, B);
+        if (variant == FLITE_ATTN_1WG) attn_fwd_kernel<1><<<grid, 192, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+        else attn_fwd_kernel<2><<<grid, 320, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+        LAUNCH_CHECK();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ((q_tiles + 1) / 2), H, B);
+    cfg.blockDim = dim3(variant == FLITE_ATTN_2CTA_1WG ? 192 : 320);
+    cfg.dynamicSmemBytes = ATT_SMEM;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (variant == FLITE_ATTN_2CTA_1WG) CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<1>, tq, tk, tv, p));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<2>, tq, tk, tv, p));
     return 0;
 }
 

@@ -48,6 +48,8 @@ extern "C" {
 #define FLITE_ATTN_AUTO 0
 #define FLITE_ATTN_1WG 1   /* one softmax warpgroup (192 threads)                 */
 #define FLITE_ATTN_2WG 2   /* two softmax warpgroups splitting the key columns    */
+#define FLITE_ATTN_2CTA_1WG 3 /* cta_group::2 pair sharing K/V, double-buffered, 1 softmax warpgroup (default) */
+#define FLITE_ATTN_2CTA_2WG 4 /* same with two softmax warpgroups                                           */
 
 int flite_abi_version(void);
 const char* flite_last_error(void);

@@ -164,7 +164,7 @@ ATT_CASES = [(1, 1, 128, 128), (1, 2, 256, 384), (2, 2, 272, 272), (2, 2, 272, 1
              (2, 12, 4112, 256)]
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("B,H,Lq,Lk", ATT_CASES)
 def test_attention_uniform(B, H, Lq, Lk, variant):
     from flite_b200 import ops
@@ -180,7 +180,8 @@ def test_attention_uniform(B, H, Lq, Lk, variant):
     assert rel(out, ref.reshape(-1, d)) <= 5e-3          # bf16 output + bf16 P, same as FA2's own error
 
 
-def test_attention_ragged_and_empty_keys():
+@pytest.mark.parametrize("variant", [1, 3, 4])
+def test_attention_ragged_and_empty_keys(variant):
     from flite_b200 import ops
     from oracle.dit_oracle import flash_attn_varlen
     H, d = 2, 512
@@ -188,7 +189,7 @@ def test_attention_ragged_and_empty_keys():
     cu_q = torch.tensor([0] + list(torch.tensor(lens_q).cumsum(0)), device=DEV, dtype=torch.int32)
     cu_k = torch.tensor([0] + list(torch.tensor(lens_k).cumsum(0)), device=DEV, dtype=torch.int32)
     q, kv = rnd(sum(lens_q), d, seed=1), rnd(sum(lens_k), 2 * d, seed=2)
-    out = ops.attention_varlen(q, kv[:, :d], kv[:, d:], cu_q, cu_k, H, max(lens_q), 256 ** -0.5)
+    out = ops.attention_varlen(q, kv[:, :d], kv[:, d:], cu_q, cu_k, H, max(lens_q), 256 ** -0.5, variant=variant)
     ok = torch.cat([torch.arange(0, 130), torch.arange(402, 407)]).to(DEV)
     cu_q2 = torch.tensor([0, 130, 135], device=DEV, dtype=torch.int32)
     cu_k2 = torch.tensor([0, 17, 317], device=DEV, dtype=torch.int32)

@@ -21,11 +21,11 @@ for (B, L, tag) in [(2, 4112, "c2"), (2, 16400, "c4")]:
     cu = torch.arange(B + 1, device=dev, dtype=torch.int32) * L
     o1 = torch.empty(B * L, d, device=dev, dtype=torch.bfloat16); o2 = torch.empty_like(o1)
     fl = 4 * B * H * L * L * 256
-    for var, o in ((1, o1), (2, o2)):
+    for var, o in ((1, o1), (3, o2), (4, o2)):
         ms = bench(lambda: ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, H, L, 256 ** -0.5, out=o, variant=var), n=5 if L > 5000 else 20)
         OUT[f"attn_{tag}_wg{var}_tflops"] = fl / ms / 1e9
         print(tag, "variant", var, "ms", ms, "TF/s", fl / ms / 1e9, flush=True)
-    OUT[f"attn_{tag}_wg2_vs_wg1_rel"] = rel(o2, o1); print("  2wg vs 1wg rel", rel(o2, o1))
+    OUT[f"attn_{tag}_cg2_vs_v1_rel"] = rel(o2, o1); print("  cg2 vs v1 rel", rel(o2, o1))
     _lib.watchdog_ok()
 # qkv epilogue
 a = (torch.randn(T, d, device=dev) * 0.5).bfloat16()
