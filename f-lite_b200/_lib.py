@@ -23,6 +23,7 @@ SIGNATURES = {
     "flite_abi_version": [],
     "flite_last_error": [],
     "flite_check_device": [],
+    "flite_set_tuning": [_I, _I],
     "flite_watchdog_status": [_P],
     "flite_cfg_euler": [_P, _I, _P, _P, _F, _F, _I, _P, _L, _P],
     "flite_rmsnorm_modulate": [_P, _L, _P, _L, _P, _I, _P, _P, _L, _I, _I, _I, _F, _P],

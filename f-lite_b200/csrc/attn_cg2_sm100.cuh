@@ -87,6 +87,7 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             for (int c = 0; c < 4; ++c)
                 tma_load_2d_cg2(smem + ATT2_SQ + c * 16384, &tmap_q, q_full, 0, p.q_col0 + h * 256 + c * 64, q_row0);
             for (int j = 0; j < n_tiles; ++j) {
+                if ((p.debug & 2) && j >= 2) break;
                 const int st = j & 1;
                 const uint32_t ph = ((j >> 1) & 1) ^ 1;
                 const int krow = k_beg + j * 128;
@@ -114,7 +115,7 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const uint32_t sv = smem_u32(smem + ATT2_SV), sp = smem_u32(smem + ATT2_SP);
             auto issue_s = [&](int j) {
                 const int st = j & 1;
-                mbar_wait<true>(&k_full[st], (j >> 1) & 1, 23);
+                if (!((p.debug & 2) && j >= 2)) mbar_wait<true>(&k_full[st], (j >> 1) & 1, 23);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (j & 1) * 128;
 #pragma unroll
@@ -133,7 +134,7 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 const int st = j & 1;
                 if (j + 1 < n_tiles) issue_s(j + 1);
                 mbar_wait<true>(p_full, j & 1, 25);
-                mbar_wait<true>(&v_full[st], (j >> 1) & 1, 26);
+                if (!((p.debug & 2) && j >= 2)) mbar_wait<true>(&v_full[st], (j >> 1) & 1, 26);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -159,6 +160,15 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait<true>(&s_full[j & 1], (j >> 1) & 1, 27);
             tc_fence_after();
+            if (p.debug & 1) {   // experiment: no softmax math, P left as is
+                if (j > 0) mbar_wait<true>(pv_done, (j - 1) & 1, 28);
+                l = 1.f;
+                tc_fence_before();
+                __syncwarp();
+                if (elect_one()) mbar_arrive_cluster(p_full, 0);
+                __syncwarp();
+                continue;
+            }
             const uint32_t ts = tmem_base + lane_off + (j & 1) * 128 + half * NC;
             const int kv_valid = min(128, k_len - j * 128) - half * NC;   // valid columns of this thread's slice
             const bool full = kv_valid >= NC;

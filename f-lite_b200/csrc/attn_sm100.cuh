@@ -28,6 +28,7 @@ struct AttnParams {
     long long ldo;
     int q_col0, k_col0, v_col0;
     float scale_log2;       // softmax_scale * log2(e)
+    int debug;              // profiling experiments only (0 in production): bit0 skip softmax math, bit1 skip K/V reloads
 };
 
 constexpr int ATT_SQ = 0, ATT_SK = 65536, ATT_SV = 131072, ATT_SP = 196608, ATT_BAR = 229376;

@@ -22,6 +22,46 @@ FLITE_DEVICE float warp_sum(float v) {
     return v;
 }
 
+
+// One 16-byte chunk (8 bf16) of  y = RMSNorm_w(x) [* (1 + scale) + shift]  with the reference's bf16 rounding points.
+// The bf16 x bf16 products / sums are done with packed HMUL2/HADD2.BF16 (exact product, one rounding) which is
+// bit-identical to "compute in fp32, round to bf16" of the torch bf16 elementwise kernels.
+FLITE_DEVICE uint4 norm_mod_chunk(const uint4& xv, float rstd, const uint4& wv, int weight_mode, bool mod,
+                                  const uint4& scv, const uint4& shv) {
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+    const uint32_t sc[4] = {scv.x, scv.y, scv.z, scv.w}, sh[4] = {shv.x, shv.y, shv.z, shv.w};
+    uint32_t out[4];
+    const __nv_bfloat162 one2 = __floats2bfloat162_rn(1.0f, 1.0f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float f0 = bf16_lo(xw[j]) * rstd, f1 = bf16_hi(xw[j]) * rstd;
+        __nv_bfloat162 n2;
+        if (weight_mode == 2) {
+            n2 = __floats2bfloat162_rn(f0 * bf16_lo(ww[j]), f1 * bf16_hi(ww[j]));       // bf16(x*rstd*w), fp32 math
+        } else {
+            n2 = __floats2bfloat162_rn(f0, f1);                                          // bf16(x*rstd)
+            if (weight_mode == 1) n2 = __hmul2(n2, *reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
+        }
+        if (mod) {
+            const __nv_bfloat162 op = __hadd2(one2, *reinterpret_cast<const __nv_bfloat162*>(&sc[j]));
+            n2 = __hadd2(__hmul2(n2, op), *reinterpret_cast<const __nv_bfloat162*>(&sh[j]));
+        }
+        out[j] = *reinterpret_cast<uint32_t*>(&n2);
+    }
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
+FLITE_DEVICE float ssq_chunk(const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(w[j]), b = bf16_hi(w[j]);
+        s = fmaf(a, a, s);
+        s = fmaf(b, b, s);
+    }
+    return s;
+}
+
 // ------------------------------------------------------------------------------------------
 // y = RMSNorm_w(x) [* (1 + scale[s]) + shift[s]]           one warp per row, d % 256 == 0
 //   weight_mode 0: no weight            (f_lite/model.py:101-108, QK-norm style)
@@ -40,39 +80,18 @@ rmsnorm_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv
     const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
     const int nchunk = d >> 3;  // 16-byte chunks per row
     float ssq = 0.f;
-    for (int c = lane; c < nchunk; c += 32) {
-        float f[8];
-        unpack8(__ldg(xr + c), f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ssq += f[j] * f[j];
-    }
+    for (int c = lane; c < nchunk; c += 32) ssq += ssq_chunk(__ldg(xr + c));
     ssq = warp_sum(ssq);
     const float rstd = rsqrtf(ssq / (float)d + eps);
     const bool mod = scale != nullptr;
     const long long s = (long long)(row / rows_per_sample) * ld_mod;
     uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
+    const uint4 z = make_uint4(0, 0, 0, 0);
     for (int c = lane; c < nchunk; c += 32) {
-        float f[8], wv[8], sc[8], sh[8];
-        unpack8(__ldg(xr + c), f);
-        if (weight_mode != 0) unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), wv);
-        if (mod) {
-            unpack8(__ldg(reinterpret_cast<const uint4*>(scale + s) + c), sc);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(shift + s) + c), sh);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float n;
-            if (weight_mode == 1) n = bf16_round(bf16_round(f[j] * rstd) * wv[j]);
-            else if (weight_mode == 2) n = bf16_round(f[j] * rstd * wv[j]);
-            else n = bf16_round(f[j] * rstd);
-            if (mod) {
-                const float one_plus = bf16_round(1.0f + sc[j]);
-                n = bf16_round(n * one_plus);
-                n = n + sh[j];
-            }
-            f[j] = n;
-        }
-        yr[c] = pack8(f);
+        const uint4 wv = weight_mode != 0 ? __ldg(reinterpret_cast<const uint4*>(w) + c) : z;
+        const uint4 scv = mod ? __ldg(reinterpret_cast<const uint4*>(scale + s) + c) : z;
+        const uint4 shv = mod ? __ldg(reinterpret_cast<const uint4*>(shift + s) + c) : z;
+        yr[c] = norm_mod_chunk(__ldg(xr + c), rstd, wv, weight_mode, mod, scv, shv);
     }
 }
 
@@ -97,41 +116,21 @@ rmsnorm_modulate_reg_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, 
     }
     float ssq = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-        float f[8];
-        unpack8(v[i], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ssq += f[j] * f[j];
-    }
+    for (int i = 0; i < MAXC; ++i) ssq += ssq_chunk(v[i]);
     ssq = warp_sum(ssq);
     const float rstd = rsqrtf(ssq / (float)d + eps);
     const bool mod = scale != nullptr;
     const long long s = (long long)(row / rows_per_sample) * ld_mod;
     uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
+    const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
         const int c = lane + 32 * i;
         if (c < nchunk) {
-            float f[8], wv[8], sc[8], sh[8];
-            unpack8(v[i], f);
-            if (weight_mode != 0) unpack8(__ldg(reinterpret_cast<const uint4*>(w) + c), wv);
-            if (mod) {
-                unpack8(__ldg(reinterpret_cast<const uint4*>(scale + s) + c), sc);
-                unpack8(__ldg(reinterpret_cast<const uint4*>(shift + s) + c), sh);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float n;
-                if (weight_mode == 1) n = bf16_round(bf16_round(f[j] * rstd) * wv[j]);
-                else if (weight_mode == 2) n = bf16_round(f[j] * rstd * wv[j]);
-                else n = bf16_round(f[j] * rstd);
-                if (mod) {
-                    n = bf16_round(n * bf16_round(1.0f + sc[j]));
-                    n = n + sh[j];
-                }
-                f[j] = n;
-            }
-            yr[c] = pack8(f);
+            const uint4 wv = weight_mode != 0 ? __ldg(reinterpret_cast<const uint4*>(w) + c) : z;
+            const uint4 scv = mod ? __ldg(reinterpret_cast<const uint4*>(scale + s) + c) : z;
+            const uint4 shv = mod ? __ldg(reinterpret_cast<const uint4*>(shift + s) + c) : z;
+            yr[c] = norm_mod_chunk(v[i], rstd, wv, weight_mode, mod, scv, shv);
         }
     }
 }

@@ -21,6 +21,7 @@ using namespace flite;
 namespace {
 
 thread_local char g_err[512] = "";
+int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // FLITE_TUNE_* knobs (A/B switches for benchmarking)
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -172,6 +173,12 @@ extern "C" {
 int flite_abi_version(void) { return FLITE_ABI_VERSION; }
 const char* flite_last_error(void) { return g_err; }
 
+int flite_set_tuning(int key, int value) {
+    if (key < 0 || key >= 8) return fail(FLITE_ERR_INVALID, "set_tuning: unknown key %d", key);
+    g_tuning[key] = value;
+    return 0;
+}
+
 int flite_check_device(void) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -224,9 +231,10 @@ int flite_rmsnorm_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, con
             (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const __nv_bfloat16*)w, weight_mode,
             (const __nv_bfloat16*)scale, (const __nv_bfloat16*)shift, ld_mod, rows_per_sample, rows, d, eps);
     };
-    if (d <= 8 * 32 * 4) launch(rmsnorm_modulate_reg_kernel<4>, 8, 256);
-    else if (d <= 8 * 32 * 12) launch(rmsnorm_modulate_reg_kernel<12>, 8, 256);
-    else if (d <= 8 * 32 * 16) launch(rmsnorm_modulate_reg_kernel<16>, 8, 256);
+    const int mode = g_tuning[FLITE_TUNE_RMSNORM_KERNEL];   // 0 auto (two-pass), 1 two-pass, 2 register-resident
+    if (mode == 2 && d <= 8 * 32 * 4) launch(rmsnorm_modulate_reg_kernel<4>, 8, 256);
+    else if (mode == 2 && d <= 8 * 32 * 12) launch(rmsnorm_modulate_reg_kernel<12>, 8, 256);
+    else if (mode == 2 && d <= 8 * 32 * 16) launch(rmsnorm_modulate_reg_kernel<16>, 8, 256);
     else launch(rmsnorm_modulate_kernel, 4, 128);
     LAUNCH_CHECK();
     return 0;
@@ -376,7 +384,7 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
     }
     if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_2CTA_2WG)
         return fail(FLITE_ERR_INVALID, "attention: unknown variant %d", variant);
-    if (variant == FLITE_ATTN_AUTO) variant = FLITE_ATTN_2CTA_1WG;
+    if (variant == FLITE_ATTN_AUTO) variant = g_tuning[FLITE_TUNE_ATTN_VARIANT] ? g_tuning[FLITE_TUNE_ATTN_VARIANT] : FLITE_ATTN_2CTA_1WG;
     const bool cg2 = variant == FLITE_ATTN_2CTA_1WG || variant == FLITE_ATTN_2CTA_2WG;
     CUtensorMap tq, tk, tv;
     int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)ldq, (uint64_t)ldq, 128);
@@ -390,6 +398,7 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
     p.out = (__nv_bfloat16*)out; p.ldo = ldo;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    p.debug = g_tuning[FLITE_TUNE_ATTN_DEBUG];
     const int q_tiles = (max_q + 127) / 128;
     if (!cg2) {
         dim3 grid(q_tiles, H, B);

@@ -51,6 +51,13 @@ extern "C" {
 #define FLITE_ATTN_2CTA_1WG 3 /* cta_group::2 pair sharing K/V, double-buffered, 1 softmax warpgroup (default) */
 #define FLITE_ATTN_2CTA_2WG 4 /* same with two softmax warpgroups                                           */
 
+/* tuning knobs (A/B switches used by the benchmarks; defaults are the measured best) */
+#define FLITE_TUNE_RMSNORM_KERNEL 0  /* 0 auto | 1 two-pass | 2 register-resident */
+#define FLITE_TUNE_ATTN_VARIANT 1    /* default attention variant when the call passes FLITE_ATTN_AUTO */
+#define FLITE_TUNE_GEMM_VARIANT 2    /* default GEMM variant when the call passes FLITE_GEMM_AUTO (0 = heuristic) */
+#define FLITE_TUNE_ATTN_DEBUG 3      /* profiling experiments only: bit0 skip softmax math, bit1 skip K/V reloads */
+int flite_set_tuning(int key, int value);
+
 int flite_abi_version(void);
 const char* flite_last_error(void);
 
