@@ -7,6 +7,8 @@
 // double-buffers K and V (loads of tile j+1 overlap the MMAs of tile j).
 //   SMEM / CTA: Q 64K | K half-tile 32K x2 | V half-tile 32K x2 | P 32K | barriers | exchange
 //   TMEM / CTA: S0 [0,128) | S1 [128,256) | O [256,512)   (own 128 query rows)
+// kPTmem: P_j is written as packed bf16 into the TMEM columns of S_j (aliased; 64 columns) and fed to the PV MMA
+// as the A operand straight from TMEM (tcgen05.mma [d], [a_tmem], b_desc) -- no shared-memory round trip for P.
 // Roles per CTA: warp 0 TMA producer (own halves; complete_tx on the leader's barriers), warp 1 MMA issuer
 // (leader CTA only; commits multicast to both CTAs), warps 2.. softmax warpgroups (as in attn_fwd_kernel).
 #pragma once
@@ -17,7 +19,7 @@ namespace flite {
 
 constexpr int ATT2_SQ = 0, ATT2_SK = 65536, ATT2_SV = 131072, ATT2_SP = 196608;
 
-template <int kWG>
+template <int kWG, bool kPTmem>
 __global__ void __launch_bounds__(64 + 128 * kWG, 1)
 attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -138,9 +140,14 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const uint64_t da = make_smem_desc_sw128(sp + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
                     const uint64_t db = make_smem_desc_sw128(sv + st * 32768 + k * 2048, 16384, 1024);
-                    umma_ss<2>(tmem_o, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);
+                    if constexpr (kPTmem) {
+                        // A = P_j: rows = lanes, 16 keys = 8 packed columns per K-step, inside S_j's columns
+                        umma_ts<2>(tmem_o, tmem_base + (j & 1) * 128 + k * 8, db, idesc_o, (j | k) != 0 ? 1u : 0u);
+                    } else {
+                        const uint64_t da = make_smem_desc_sw128(sp + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+                        umma_ss<2>(tmem_o, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit_cg2(&v_empty[st], 0x3);
                 umma_commit_cg2(pv_done, 0x3);
@@ -224,7 +231,9 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
             l = l * corr + (rs0 + rs1);
             // P_{j-1} V_{j-1} must be complete before P (smem) or O (TMEM) are touched
-            if (j > 0) {
+            // smem P: P_{j-1} V_{j-1} must be complete before P is overwritten.  TMEM P lives in S_j's own columns,
+            // so only an O rescale has to wait for the previous PV.
+            if (j > 0 && (!kPTmem || need_any)) {
                 mbar_wait<true>(pv_done, (j - 1) & 1, 28);
                 tc_fence_after();
                 if (need_any) {
@@ -240,15 +249,24 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     tmem_st_wait();
                 }
             }
-            // write P (bf16, K-major, 128B swizzle): 64-key chunks of [128 rows x 128 B]
-            uint8_t* sp_row = smem + ATT2_SP + r * 128 + ((kWG == 2) ? half * 16384 : 0);
+            if constexpr (kPTmem) {
+                // P (packed bf16 pairs) over the first 64 columns of S_j.  Every thread of this row group has
+                // finished its tcgen05.ld of S_j (kWG == 2: guaranteed by the row-max exchange barrier above).
+                const uint32_t tp = tmem_base + lane_off + (j & 1) * 128 + half * (NC / 2);
 #pragma unroll
-            for (int u = 0; u < NC / 8; ++u) {
-                const int chunk = u >> 3, unit = u & 7;
-                uint4 v = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                *reinterpret_cast<uint4*>(sp_row + chunk * 16384 + ((unit ^ (r & 7)) << 4)) = v;
+                for (int c = 0; c < NC / 64; ++c) tmem_st_x32(tp + c * 32, pk + c * 32);
+                tmem_st_wait();
+            } else {
+                // write P (bf16, K-major, 128B swizzle): 64-key chunks of [128 rows x 128 B]
+                uint8_t* sp_row = smem + ATT2_SP + r * 128 + ((kWG == 2) ? half * 16384 : 0);
+#pragma unroll
+                for (int u = 0; u < NC / 8; ++u) {
+                    const int chunk = u >> 3, unit = u & 7;
+                    uint4 v = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                    *reinterpret_cast<uint4*>(sp_row + chunk * 16384 + ((unit ^ (r & 7)) << 4)) = v;
+                }
+                fence_proxy_async_smem();
             }
-            fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (elect_one()) mbar_arrive_cluster(p_full, 0);   // P of both CTAs is consumed by the leader's MMAs

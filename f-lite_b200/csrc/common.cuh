@@ -255,16 +255,28 @@ FLITE_DEVICE void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uin
     }
 }
 
-// A operand from TMEM (bf16 packed two per 32-bit column), B from smem.
+// A operand from TMEM (bf16 packed two per 32-bit column, one row per lane), B from smem.
+template <int kCtaGroup>
 FLITE_DEVICE void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if constexpr (kCtaGroup == 1) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 
 // tcgen05.commit: the mbarrier gets one arrival when all prior MMAs of this thread have completed.

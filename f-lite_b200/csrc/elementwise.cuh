@@ -24,8 +24,8 @@ FLITE_DEVICE float warp_sum(float v) {
 
 
 // One 16-byte chunk (8 bf16) of  y = RMSNorm_w(x) [* (1 + scale) + shift]  with the reference's bf16 rounding points.
-// The bf16 x bf16 products / sums are done with packed HMUL2/HADD2.BF16 (exact product, one rounding) which is
-// bit-identical to "compute in fp32, round to bf16" of the torch bf16 elementwise kernels.
+// The bf16 x bf16 products / sums are done with packed mul.rn / add.rn.bf16x2 (never contracted into an FMA:
+// exact product, one rounding) which is bit-identical to "compute in fp32, round to bf16" of the torch bf16 elementwise kernels.
 FLITE_DEVICE uint4 norm_mod_chunk(const uint4& xv, float rstd, const uint4& wv, int weight_mode, bool mod,
                                   const uint4& scv, const uint4& shv) {
     const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
@@ -40,11 +40,11 @@ FLITE_DEVICE uint4 norm_mod_chunk(const uint4& xv, float rstd, const uint4& wv, 
             n2 = __floats2bfloat162_rn(f0 * bf16_lo(ww[j]), f1 * bf16_hi(ww[j]));       // bf16(x*rstd*w), fp32 math
         } else {
             n2 = __floats2bfloat162_rn(f0, f1);                                          // bf16(x*rstd)
-            if (weight_mode == 1) n2 = __hmul2(n2, *reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
+            if (weight_mode == 1) n2 = __hmul2_rn(n2, *reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
         }
         if (mod) {
-            const __nv_bfloat162 op = __hadd2(one2, *reinterpret_cast<const __nv_bfloat162*>(&sc[j]));
-            n2 = __hadd2(__hmul2(n2, op), *reinterpret_cast<const __nv_bfloat162*>(&sh[j]));
+            const __nv_bfloat162 op = __hadd2_rn(one2, *reinterpret_cast<const __nv_bfloat162*>(&sc[j]));
+            n2 = __hadd2_rn(__hmul2_rn(n2, op), *reinterpret_cast<const __nv_bfloat162*>(&sh[j]));
         }
         out[j] = *reinterpret_cast<uint32_t*>(&n2);
     }

@@ -378,14 +378,16 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_cg2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_cg2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_cg2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_cg2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_cg2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_cg2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         configured = true;
     }
-    if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_2CTA_2WG)
+    if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_2CTA_2WG_PTMEM)
         return fail(FLITE_ERR_INVALID, "attention: unknown variant %d", variant);
     if (variant == FLITE_ATTN_AUTO) variant = g_tuning[FLITE_TUNE_ATTN_VARIANT] ? g_tuning[FLITE_TUNE_ATTN_VARIANT] : FLITE_ATTN_2CTA_1WG;
-    const bool cg2 = variant == FLITE_ATTN_2CTA_1WG || variant == FLITE_ATTN_2CTA_2WG;
+    const bool cg2 = variant >= FLITE_ATTN_2CTA_1WG;
     CUtensorMap tq, tk, tv;
     int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)ldq, (uint64_t)ldq, 128);
     if (rc) return rc;
@@ -409,7 +411,8 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * ((q_tiles + 1) / 2), H, B);
-    cfg.blockDim = dim3(variant == FLITE_ATTN_2CTA_1WG ? 192 : 320);
+    const bool one_wg = variant == FLITE_ATTN_2CTA_1WG || variant == FLITE_ATTN_2CTA_1WG_PTMEM;
+    cfg.blockDim = dim3(one_wg ? 192 : 320);
     cfg.dynamicSmemBytes = ATT_SMEM;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
@@ -419,8 +422,12 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (variant == FLITE_ATTN_2CTA_1WG) CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<1>, tq, tk, tv, p));
-    else CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<2>, tq, tk, tv, p));
+    switch (variant) {
+        case FLITE_ATTN_2CTA_1WG: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<1, false>, tq, tk, tv, p)); break;
+        case FLITE_ATTN_2CTA_2WG: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<2, false>, tq, tk, tv, p)); break;
+        case FLITE_ATTN_2CTA_1WG_PTMEM: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<1, true>, tq, tk, tv, p)); break;
+        default: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<2, true>, tq, tk, tv, p)); break;
+    }
     return 0;
 }
 

@@ -50,6 +50,8 @@ extern "C" {
 #define FLITE_ATTN_2WG 2   /* two softmax warpgroups splitting the key columns    */
 #define FLITE_ATTN_2CTA_1WG 3 /* cta_group::2 pair sharing K/V, double-buffered, 1 softmax warpgroup (default) */
 #define FLITE_ATTN_2CTA_2WG 4 /* same with two softmax warpgroups                                           */
+#define FLITE_ATTN_2CTA_1WG_PTMEM 5 /* cta_group::2, P kept in TMEM (A operand of the PV MMA read from TMEM)    */
+#define FLITE_ATTN_2CTA_2WG_PTMEM 6
 
 /* tuning knobs (A/B switches used by the benchmarks; defaults are the measured best) */
 #define FLITE_TUNE_RMSNORM_KERNEL 0  /* 0 auto | 1 two-pass | 2 register-resident */
