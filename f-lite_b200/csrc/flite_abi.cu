@@ -386,7 +386,7 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
     }
     if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_2CTA_2WG_PTMEM)
         return fail(FLITE_ERR_INVALID, "attention: unknown variant %d", variant);
-    if (variant == FLITE_ATTN_AUTO) variant = g_tuning[FLITE_TUNE_ATTN_VARIANT] ? g_tuning[FLITE_TUNE_ATTN_VARIANT] : FLITE_ATTN_2CTA_1WG;
+    if (variant == FLITE_ATTN_AUTO) variant = g_tuning[FLITE_TUNE_ATTN_VARIANT] ? g_tuning[FLITE_TUNE_ATTN_VARIANT] : FLITE_ATTN_2CTA_1WG_PTMEM;
     const bool cg2 = variant >= FLITE_ATTN_2CTA_1WG;
     CUtensorMap tq, tk, tv;
     int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)ldq, (uint64_t)ldq, 128);

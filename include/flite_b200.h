@@ -48,9 +48,9 @@ extern "C" {
 #define FLITE_ATTN_AUTO 0
 #define FLITE_ATTN_1WG 1   /* one softmax warpgroup (192 threads)                 */
 #define FLITE_ATTN_2WG 2   /* two softmax warpgroups splitting the key columns    */
-#define FLITE_ATTN_2CTA_1WG 3 /* cta_group::2 pair sharing K/V, double-buffered, 1 softmax warpgroup (default) */
+#define FLITE_ATTN_2CTA_1WG 3 /* cta_group::2 pair sharing K/V, double-buffered, 1 softmax warpgroup */
 #define FLITE_ATTN_2CTA_2WG 4 /* same with two softmax warpgroups                                           */
-#define FLITE_ATTN_2CTA_1WG_PTMEM 5 /* cta_group::2, P kept in TMEM (A operand of the PV MMA read from TMEM)    */
+#define FLITE_ATTN_2CTA_1WG_PTMEM 5 /* cta_group::2, P kept in TMEM (A operand of the PV MMA read from TMEM); default */
 #define FLITE_ATTN_2CTA_2WG_PTMEM 6
 
 /* tuning knobs (A/B switches used by the benchmarks; defaults are the measured best) */
