@@ -28,12 +28,13 @@ SIGNATURES = {
     "flite_cfg_euler": [_P, _I, _P, _P, _F, _F, _I, _P, _L, _P],
     "flite_rmsnorm_modulate": [_P, _L, _P, _L, _P, _I, _P, _P, _L, _I, _I, _I, _F, _P],
     "flite_rope_qknorm": [_P, _L, _I, _I, _P, _P, _I, _F, _P],
-    "flite_patch_embed": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "flite_patch_embed": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "flite_permute_021": [_P, _P, _I, _I, _I, _P],
     "flite_timestep_embed": [_P, _I, _P, _P, _I, _I, _P],
     "flite_unpatchify": [_P, _L, _P, _I, _I, _I, _I, _I, _I, _P],
     "flite_pack_context": [_P, _L, _P, _L, _P, _I, _I, _I, _P, _P, _P, _P],
     "flite_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _I, _I, _P, _L, _P, _L, _I, _P, _P, _I, _F,
-                        _I, _P],
+                        _I, _I, _I, _P],
     "flite_attention_varlen": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _I, _F, _I, _P],
 }
 

@@ -190,16 +190,19 @@ template <int KDIM>
 __global__ void __launch_bounds__(256)
 patch_embed_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                    const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ reg_tokens,
-                   __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int P, int d, int n_reg) {
+                   __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int P, int d, int n_reg,
+                   int tok_offset, int tok_count) {
+    // rows of `out` are (sample, local token); local token t is sequence position tok_offset + t (sequence-parallel
+    // ranks embed only their own slice; tok_offset = 0, tok_count = L otherwise)
     __shared__ float patch[PE_TOK][KDIM + 1];
-    const int hp = H / P, wp = W / P, hw = hp * wp, L = n_reg + hw;
-    const int tok0 = blockIdx.x * PE_TOK;           // index over B * L rows
+    const int wp = W / P, L = tok_count;
+    const int tok0 = blockIdx.x * PE_TOK;           // index over B * tok_count rows
     for (int i = threadIdx.x; i < PE_TOK * KDIM; i += 256) {
         const int t = i / KDIM, k = i % KDIM;
         const int r = tok0 + t;
         float v = 0.f;
         if (r < B * L) {
-            const int b = r / L, l = r % L;
+            const int b = r / L, l = tok_offset + r % L;
             if (l >= n_reg) {
                 const int pi = l - n_reg, hy = pi / wp, wx = pi % wp;
                 const int c = k / (P * P), p1 = (k / P) % P, p2 = k % P;
@@ -219,7 +222,7 @@ patch_embed_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         for (int t = 0; t < PE_TOK; ++t) {
             const int r = tok0 + t;
             if (r >= B * L) break;
-            const int l = r % L;
+            const int l = tok_offset + r % L;
             if (l < n_reg) {
                 out[(long long)r * d + n] = reg_tokens[(long long)l * d + n];
             } else {
@@ -316,6 +319,21 @@ pack_rows_kernel(const __nv_bfloat16* __restrict__ src, long long lds, __nv_bflo
     const uint4* s = reinterpret_cast<const uint4*>(src + (long long)r * lds);
     uint4* t = reinterpret_cast<uint4*>(dst + (long long)(cu[b] + pp) * ldd);
     for (int c = threadIdx.x; c < (d >> 3); c += 128) t[c] = __ldg(s + c);
+}
+
+// ------------------------------------------------------------------------------------------
+// [n0, n1, n2] -> [n1, n0, n2] copy of bf16 rows (n2 % 8 == 0): layout transform around the Ulysses all-to-alls.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+permute_021_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n0, int n1, int n2v) {
+    const long long total = (long long)n0 * n1 * n2v;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % n2v);
+        const long long t = i / n2v;
+        const int b = (int)(t % n0), a = (int)(t / n0);      // dst index (a in n1, b in n0, c)
+        dst[i] = __ldg(src + ((long long)b * n1 + a) * n2v + c);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

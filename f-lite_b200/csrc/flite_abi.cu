@@ -256,16 +256,19 @@ int flite_rope_qknorm(void* buf, int64_t ld, int rows, int n_slots, const void* 
 }
 
 int flite_patch_embed(const void* x, const void* w, const void* bias, const void* reg_tokens, void* out, int B, int C,
-                      int H, int W, int P, int d, int n_reg, void* stream) {
+                      int H, int W, int P, int d, int n_reg, int tok_offset, int tok_count, void* stream) {
     if (!x || !w || !bias || !out || (n_reg > 0 && !reg_tokens)) return fail(FLITE_ERR_INVALID, "patch_embed: null pointer");
     if (H % P || W % P) return fail(FLITE_ERR_INVALID, "patch_embed: H, W must be multiples of the patch size");
     const int kdim = C * P * P;
-    const int rows = B * (n_reg + (H / P) * (W / P));
+    const int L_full = n_reg + (H / P) * (W / P);
+    if (tok_count <= 0) { tok_offset = 0; tok_count = L_full; }
+    if (tok_offset < 0 || tok_offset + tok_count > L_full) return fail(FLITE_ERR_INVALID, "patch_embed: token slice out of range");
+    const int rows = B * tok_count;
     const int blocks = (rows + PE_TOK - 1) / PE_TOK;
     auto args = [&](auto kern) {
         kern<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
                                                       (const __nv_bfloat16*)bias, (const __nv_bfloat16*)reg_tokens,
-                                                      (__nv_bfloat16*)out, B, C, H, W, P, d, n_reg);
+                                                      (__nv_bfloat16*)out, B, C, H, W, P, d, n_reg, tok_offset, tok_count);
     };
     if (kdim == 64) args(patch_embed_kernel<64>);
     else if (kdim == 16) args(patch_embed_kernel<16>);
@@ -293,6 +296,18 @@ int flite_unpatchify(const void* tok, int64_t ldt, void* out, int B, int C, int 
     return 0;
 }
 
+int flite_permute_021(const void* src, void* dst, int n0, int n1, int n2, void* stream) {
+    if (!src || !dst) return fail(FLITE_ERR_INVALID, "permute: null pointer");
+    if (n2 % 8) return fail(FLITE_ERR_INVALID, "permute: innermost extent must be a multiple of 8");
+    const long long total = (long long)n0 * n1 * (n2 / 8);
+    if (total <= 0) return 0;
+    long long blocks = (total + 255) / 256;
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    permute_021_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, n0, n1, n2 / 8);
+    LAUNCH_CHECK();
+    return 0;
+}
+
 int flite_pack_context(const void* src, int64_t lds, void* dst, int64_t ldd, const float* mask, int B, int Lc, int d,
                        int* pos_ws, int* seqlens_ws, int* cu_seqlens, void* stream) {
     if (!src || !dst || !mask || !pos_ws || !seqlens_ws || !cu_seqlens) return fail(FLITE_ERR_INVALID, "pack_context: null pointer");
@@ -310,7 +325,7 @@ int flite_pack_context(const void* src, int64_t lds, void* dst, int64_t ldd, con
 int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
                     const void* bias, int act, int epilogue, const void* resid, int64_t ldr, const void* gate,
                     int64_t ld_gate, int rows_per_sample, const void* rope_cos, const void* rope_sin, int qk_cols,
-                    float eps, int variant, void* stream) {
+                    float eps, int sp_ranks, int sp_heads_per_rank, int variant, void* stream) {
     if (!A || !W || !C) return fail(FLITE_ERR_INVALID, "gemm: null pointer");
     if (M <= 0) return 0;
     if (K <= 0 || K % 64) return fail(FLITE_ERR_INVALID, "gemm: K = %d must be a positive multiple of 64", K);
@@ -324,7 +339,11 @@ int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
     if (epilogue == EPI_QKV_ROPE && ((rope_cos == nullptr) != (rope_sin == nullptr) || qk_cols % 256))
         return fail(FLITE_ERR_INVALID, "gemm: bad RoPE arguments");
     if (rows_per_sample <= 0) rows_per_sample = M;
+    if (sp_ranks > 0 && (epilogue != EPI_QKV_ROPE || sp_heads_per_rank <= 0 || N % 768 ||
+                         (N / 768) != sp_ranks * sp_heads_per_rank || M % rows_per_sample))
+        return fail(FLITE_ERR_INVALID, "gemm: sequence-parallel head scatter needs the QKV epilogue and N = 3*256*ranks*heads_per_rank");
 
+    if (variant == FLITE_GEMM_AUTO && g_tuning[FLITE_TUNE_GEMM_VARIANT]) variant = g_tuning[FLITE_TUNE_GEMM_VARIANT];
     if (variant == FLITE_GEMM_AUTO) {
         if (epilogue == EPI_QKV_ROPE) variant = (M > 128) ? FLITE_GEMM_2CTA_N256 : FLITE_GEMM_1CTA_N256;
         else if (N % 256 == 0 && M > 128) variant = FLITE_GEMM_2CTA_N256;
@@ -350,6 +369,7 @@ int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
     p.gate = (const __nv_bfloat16*)gate; p.ld_gate = ld_gate;
     p.rows_per_sample = rows_per_sample;
     p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin; p.qk_cols = qk_cols; p.eps = eps;
+    p.sp_ranks = sp_ranks; p.sp_hp = sp_heads_per_rank; p.n_heads = N / 768;
 
     CUtensorMap ta, tb;
     int rc = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128);

@@ -38,6 +38,11 @@ struct GemmParams {
     const __nv_bfloat16* rope_sin;
     int qk_cols;                 // columns [0, qk_cols) get RoPE (if tables != null) + RMSNorm; rest plain
     float eps;
+    // EPI_QKV_ROPE, Ulysses sequence parallelism: write each head straight into the all-to-all send layout
+    // [sample][dest rank][local token][q|k|v][head % sp_hp][256]  (sp_ranks == 0: plain row-major [M, N])
+    int sp_ranks;
+    int sp_hp;                   // heads per rank
+    int n_heads;
 };
 
 constexpr int GEMM_BLOCK_K = 64;
@@ -334,7 +339,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 __syncwarp();
                 if (row_ok) {
                     const float rstd = do_norm ? rsqrtf(ssq * (1.0f / 256.0f) + p.eps) : 1.0f;
-                    uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + n0);
+                    long long out_off = (long long)row * p.ldc + n0;
+                    if (p.sp_ranks > 0) {
+                        const int t = n0 >> 8, which = t / p.n_heads, head = t % p.n_heads;
+                        const int smp = row / p.rows_per_sample, li = row % p.rows_per_sample;
+                        const long long drow = ((long long)smp * p.sp_ranks + head / p.sp_hp) * p.rows_per_sample + li;
+                        out_off = drow * p.ldc + (long long)which * p.sp_hp * 256 + (head % p.sp_hp) * 256;
+                    }
+                    uint4* cp = reinterpret_cast<uint4*>(p.C + out_off);
 #pragma unroll
                     for (int u = 0; u < 32; ++u) {
                         uint32_t o[4];

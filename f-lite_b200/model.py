@@ -181,6 +181,7 @@ class DiT(nn.Module):
         self._freqs = None
         self.hoist_context = True
         self.gemm_variant = GEMM_AUTO
+        self.sp_group = None      # Ulysses sequence-parallel process group (see enable_sequence_parallel)
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -190,6 +191,17 @@ class DiT(nn.Module):
     @property
     def device(self):
         return self.context_proj.weight.device
+
+    def enable_sequence_parallel(self, group):
+        """Ulysses sequence parallelism over ``group``: every rank holds
+        L/P tokens of each sequence; self-attention is computed head-sharded over the full sequence with two
+        all-to-alls per block (NCCL over NVLink); everything else is token-local.  ``None`` disables it."""
+        if group is not None:
+            import torch.distributed as dist
+            P = dist.get_world_size(group)
+            if self.config.num_heads % P:
+                raise FliteError(f"sequence parallel degree {P} must divide num_heads {self.config.num_heads}")
+        self.sp_group = group
 
     def _check_ready(self):
         w = self.context_proj.weight
@@ -204,6 +216,13 @@ class DiT(nn.Module):
             hd = self.config.hidden_size // self.config.num_heads
             cos, sin = _rope_table(hd, h, w, self.config.rope_base, N_REGISTER, round_bf16=True)
             self._rope_cache[key] = (cos.to(device, torch.bfloat16), sin.to(device, torch.bfloat16))
+        return self._rope_cache[key]
+
+    def _rope_slice(self, h, w, device, l0, n):
+        key = (h, w, str(device), l0, n)
+        if key not in self._rope_cache:
+            cos, sin = self._rope(h, w, device)
+            self._rope_cache[key] = (cos[l0:l0 + n].contiguous(), sin[l0:l0 + n].contiguous())
         return self._rope_cache[key]
 
     def _gate_up(self, i, blk):
@@ -274,23 +293,40 @@ class DiT(nn.Module):
         B, C, H, W = x.shape
         hp, wp = H // p, W // p
         L = N_REGISTER + hp * wp
-        T = B * L
         v = self.gemm_variant
 
         ctx = self._context(context, context_attn_mask)
         if ctx.B != B:
             raise FliteError(f"context batch {ctx.B} != latent batch {B}")
 
+        # --- sequence-parallel layout: this rank owns tokens [l0, l0 + Lq) of every sequence
+        sp = self.sp_group
+        if sp is not None:
+            import torch.distributed as dist
+            P, rk = dist.get_world_size(sp), dist.get_rank(sp)
+            if L % P:
+                raise FliteError(f"sequence length {L} is not divisible by the sequence-parallel degree {P}")
+            Lq, l0 = L // P, rk * (L // P)
+        else:
+            P, rk, Lq, l0 = 1, 0, L, 0
+        T = B * Lq
+
         # --- tokens: patchify + register tokens (model.py:533-535)
         xin = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
         xs = self._buf("x", (T, d), dev)
         ops.patch_embed(xin.contiguous(), self.patch_embed.patch_proj.weight, self.patch_embed.patch_proj.bias,
-                        self.register_tokens, p, out=xs)
-        cos, sin = self._rope(hp, wp, dev)
-        cu_x = self._ws.get(("cu_x", B, L))
+                        self.register_tokens, p, out=xs, tok_offset=l0, tok_count=Lq)
+        cos, sin = self._rope_slice(hp, wp, dev, l0, Lq)
+        cu_x = self._ws.get(("cu_x", B, Lq))
         if cu_x is None or cu_x.device != dev:
-            cu_x = (torch.arange(0, B + 1, dtype=torch.int32) * L).to(dev)
-            self._ws[("cu_x", B, L)] = cu_x
+            cu_x = (torch.arange(0, B + 1, dtype=torch.int32) * Lq).to(dev)
+            self._ws[("cu_x", B, Lq)] = cu_x
+        cu_full = cu_x
+        if sp is not None:
+            cu_full = self._ws.get(("cu_x", B, L))
+            if cu_full is None or cu_full.device != dev:
+                cu_full = (torch.arange(0, B + 1, dtype=torch.int32) * L).to(dev)
+                self._ws[("cu_x", B, L)] = cu_full
 
         # --- timestep path (model.py:551-556,578): sinusoid -> MLP -> SiLU -> adaLN / final modulation
         if self._freqs is None or self._freqs.device != dev:
@@ -315,42 +351,71 @@ class DiT(nn.Module):
             mod[:, k * d:(k + 1) * d] for k in range(9))
 
         nbuf = self._buf("n", (T, d), dev)
-        qkv = self._buf("qkv", (T, 3 * d), dev)
         abuf = self._buf("attn", (T, d), dev)
         qc = self._buf("qc", (T, d), dev)
         inter = self.blocks[0].mlp.gate_proj.weight.shape[0] if len(self.blocks) else 0
         hmid = self._buf("hmid", (T, inter), dev)
         scale = (d // nh) ** -0.5
+        if sp is None:
+            qkv = self._buf("qkv", (T, 3 * d), dev)
+        else:
+            hq, dq = nh // P, d // P                                 # heads / width of this rank's head group
+            a2a_send = self._buf("a2a_send", (B, P * Lq, 3 * dq), dev)   # [sample][dest rank][local token][q|k|v]
+            a2a_recv = self._buf("a2a_recv", (B, L, 3 * dq), dev)        # [sample][full sequence][q|k|v of my heads]
+            ao_full = self._buf("ao_full", (B, L, dq), dev)
+            ao_recv = self._buf("ao_recv", (B, P, Lq * dq), dev)         # [sample][source rank][local token, head group]
 
         for i, blk in enumerate(self.blocks):
             # ---- self-attention (model.py:283-289)
-            ops.rmsnorm_modulate(xs, blk.norm1.weight, 1, scale_sa, shift_sa, rows_per_sample=L, out=nbuf)
+            ops.rmsnorm_modulate(xs, blk.norm1.weight, 1, scale_sa, shift_sa, rows_per_sample=Lq, out=nbuf)
             sa = blk.self_attn
-            ops.gemm(nbuf, sa.qkv.weight, sa.qkv.bias, epilogue=EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin,
-                     qk_cols=2 * d, rows_per_sample=L, variant=v, out=qkv)
-            ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu_x, cu_x, nh, L, scale, out=abuf)
+            if sp is None:
+                ops.gemm(nbuf, sa.qkv.weight, sa.qkv.bias, epilogue=EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin,
+                         qk_cols=2 * d, rows_per_sample=Lq, variant=v, out=qkv)
+                ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu_x, cu_x, nh, L, scale, out=abuf)
+            else:
+                # Ulysses: the QKV epilogue scatters heads into the all-to-all send layout; after the exchange this
+                # rank holds q|k|v of its hq heads for the FULL sequence; the second exchange returns the outputs.
+                ops.gemm(nbuf, sa.qkv.weight, sa.qkv.bias, epilogue=EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin,
+                         qk_cols=2 * d, rows_per_sample=Lq, variant=v, out=a2a_send.view(B * P * Lq, 3 * dq),
+                         sp_ranks=P, sp_heads_per_rank=hq)
+                for b in range(B):
+                    dist.all_to_all_single(a2a_recv[b], a2a_send[b], group=sp)
+                r2 = a2a_recv.view(B * L, 3 * dq)
+                ops.attention_varlen(r2[:, :dq], r2[:, dq:2 * dq], r2[:, 2 * dq:], cu_full, cu_full, hq, L, scale,
+                                     out=ao_full.view(B * L, dq))
+                for b in range(B):
+                    dist.all_to_all_single(ao_recv[b], ao_full[b], group=sp)
+                for b in range(B):   # [source rank][token][dq] -> [token][source rank * dq] = head-major columns
+                    ops.permute_021(ao_recv[b].view(P, Lq, dq), out=abuf[b * Lq:(b + 1) * Lq].view(Lq, P, dq))
             ops.gemm(abuf, sa.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_sa,
-                     rows_per_sample=L, variant=v, out=xs)
-            # ---- cross-attention (model.py:291-297)
+                     rows_per_sample=Lq, variant=v, out=xs)
+            # ---- cross-attention (model.py:291-297): token-local, context K/V replicated
             if blk.cross_attn is not None:
                 ca = blk.cross_attn
-                ops.rmsnorm_modulate(xs, blk.norm2.weight, 1, scale_ca, shift_ca, rows_per_sample=L, out=nbuf)
-                ops.gemm(nbuf, ca.q.weight, ca.q.bias, epilogue=EPI_QKV_ROPE, qk_cols=d, rows_per_sample=L,
+                ops.rmsnorm_modulate(xs, blk.norm2.weight, 1, scale_ca, shift_ca, rows_per_sample=Lq, out=nbuf)
+                ops.gemm(nbuf, ca.q.weight, ca.q.bias, epilogue=EPI_QKV_ROPE, qk_cols=d, rows_per_sample=Lq,
                          variant=v, out=qc)
                 kv = ctx.kvs[i]
-                ops.attention_varlen(qc, kv[:, :d], kv[:, d:], cu_x, ctx.cu_k, nh, L, scale, out=abuf)
+                ops.attention_varlen(qc, kv[:, :d], kv[:, d:], cu_x, ctx.cu_k, nh, Lq, scale, out=abuf)
                 ops.gemm(abuf, ca.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_ca,
-                         rows_per_sample=L, variant=v, out=xs)
+                         rows_per_sample=Lq, variant=v, out=xs)
             # ---- SwiGLU MLP (model.py:299-301)
-            ops.rmsnorm_modulate(xs, blk.norm3.weight, 1, scale_mlp, shift_mlp, rows_per_sample=L, out=nbuf)
+            ops.rmsnorm_modulate(xs, blk.norm3.weight, 1, scale_mlp, shift_mlp, rows_per_sample=Lq, out=nbuf)
             ops.gemm(nbuf, self._gate_up(i, blk), None, epilogue=EPI_SWIGLU, variant=v, out=hmid)
             ops.gemm(hmid, blk.mlp.down_proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_mlp,
-                     rows_per_sample=L, variant=v, out=xs)
+                     rows_per_sample=Lq, variant=v, out=xs)
 
         # ---- final head (model.py:577-590)
         fshift, fscale = fmod[:, :d], fmod[:, d:]
         fw = self.final_norm.weight
-        ops.rmsnorm_modulate(xs, fw, 2 if fw is not None else 0, fscale, fshift, rows_per_sample=L, out=nbuf)
+        ops.rmsnorm_modulate(xs, fw, 2 if fw is not None else 0, fscale, fshift, rows_per_sample=Lq, out=nbuf)
         o = ops.gemm(nbuf, self.final_proj.weight, self.final_proj.bias, variant=v)
+        if sp is not None:
+            # gather every rank's token slice: [rank][sample][Lq*64] -> [sample][rank][Lq*64] = [B*L, 64]
+            no = o.shape[1]
+            gathered = torch.empty((P, B, Lq * no), dtype=torch.bfloat16, device=dev)
+            dist.all_gather_into_tensor(gathered.view(P * B * Lq, no), o, group=sp)
+            o = ops.permute_021(gathered).view(B * L, no)
         out = ops.unpatchify(o, B, C, H, W, p, N_REGISTER)
         return out if x.dtype == torch.bfloat16 else out.to(x.dtype)

@@ -93,7 +93,7 @@ def rope_qknorm_(buf: torch.Tensor, n_slots: int, cos: Optional[torch.Tensor], s
 
 
 def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, reg_tokens: torch.Tensor, patch: int,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, tok_offset: int = 0, tok_count: int = 0) -> torch.Tensor:
     lib = _lib.load()
     for t, n in ((x, "x"), (weight, "weight"), (bias, "bias"), (reg_tokens, "register_tokens")):
         _chk(t, n)
@@ -102,11 +102,12 @@ def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, reg_t
     B, C, H, W = x.shape
     d = weight.shape[0]
     n_reg = reg_tokens.shape[-2]
-    rows = B * (n_reg + (H // patch) * (W // patch))
+    rows = B * (tok_count if tok_count > 0 else n_reg + (H // patch) * (W // patch))
     if out is None:
         out = torch.empty((rows, d), dtype=BF16, device=x.device)
     _lib.check(lib.flite_patch_embed(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), reg_tokens.data_ptr(),
-                                     out.data_ptr(), B, C, H, W, patch, d, n_reg, _stream()), "patch_embed")
+                                     out.data_ptr(), B, C, H, W, patch, d, n_reg, tok_offset, tok_count, _stream()),
+               "patch_embed")
     LAUNCHES[0] += 1
     return out
 
@@ -158,7 +159,8 @@ def pack_context(src: torch.Tensor, mask_f32: torch.Tensor):
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = 0,
          epilogue: int = EPI_STORE, resid: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
          rows_per_sample: int = 0, rope_cos: Optional[torch.Tensor] = None, rope_sin: Optional[torch.Tensor] = None,
-         qk_cols: int = 0, eps: float = 1e-6, variant: int = GEMM_AUTO, out: Optional[torch.Tensor] = None):
+         qk_cols: int = 0, eps: float = 1e-6, variant: int = GEMM_AUTO, out: Optional[torch.Tensor] = None,
+         sp_ranks: int = 0, sp_heads_per_rank: int = 0):
     """out = epilogue(a @ w.T); a [M, K], w [N, K] (nn.Linear layout), bf16."""
     lib = _lib.load()
     _chk(a, "a")
@@ -167,6 +169,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     N = w.shape[0]
     n_out = N // 2 if epilogue == EPI_SWIGLU else N
     if out is None:
+        if sp_ranks > 0:
+            raise _lib.FliteError("gemm: the sequence-parallel head scatter needs an explicit output buffer")
         out = torch.empty((M, n_out), dtype=BF16, device=a.device)
     _chk(out, "out")
     for t, n in ((bias, "bias"), (resid, "resid"), (gate, "gate")):
@@ -184,7 +188,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
                                    out.stride(0), M, N, K, _ptr(bias), act, epilogue, _ptr(resid),
                                    resid.stride(0) if resid is not None else 0, _ptr(gate),
                                    gate.stride(0) if gate is not None else 0, rows_per_sample, _ptr(rope_cos),
-                                   _ptr(rope_sin), qk_cols, eps, variant, _stream()), "gemm_bf16")
+                                   _ptr(rope_sin), qk_cols, eps, sp_ranks, sp_heads_per_rank, variant, _stream()),
+               "gemm_bf16")
     LAUNCHES[0] += 1
     if hook is not None:
         hook("gemm", "end", (M, N, K, epilogue))
@@ -208,6 +213,20 @@ def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: to
                                           v.data_ptr(), v.stride(0), 0, out.data_ptr(), out.stride(0),
                                           cu_q.data_ptr(), cu_k.data_ptr(), B, num_heads, max_q,
                                           float(softmax_scale), variant, _stream()), "attention_varlen")
+    LAUNCHES[0] += 1
+    return out
+
+
+def permute_021(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[n0, n1, n2] -> [n1, n0, n2] (bf16 contiguous, n2 % 8 == 0)."""
+    lib = _lib.load()
+    _chk(src, "src")
+    if not src.is_contiguous() or src.dim() != 3:
+        raise _lib.FliteError("permute_021 needs a contiguous 3-D tensor")
+    n0, n1, n2 = src.shape
+    if out is None:
+        out = torch.empty((n1, n0, n2), dtype=BF16, device=src.device)
+    _lib.check(lib.flite_permute_021(src.data_ptr(), out.data_ptr(), n0, n1, n2, _stream()), "permute_021")
     LAUNCHES[0] += 1
     return out
 

@@ -54,11 +54,22 @@ def time_shift_schedule(num_inference_steps: int, alpha: float):
 
 @torch.no_grad()
 def denoise_step(dit_model, latents, acc, context_input, mask_input, t_tensor, dt: float, guidance_scale: float,
-                 do_cfg: bool = True):
+                 do_cfg: bool = True, cfg_group=None):
     """One denoise step: CFG-batched DiT forward ([negative, positive], pipeline.py:264-271) followed by the
     fused CFG-combine + Euler update.  ``acc`` (bf16 or fp32) and ``latents`` (bf16) are updated in place.
-    ``t_tensor`` holds the (already time-shifted) t for every model row, in the model dtype (pipeline.py:260)."""
+    ``t_tensor`` holds the (already time-shifted) t for every model row, in the model dtype (pipeline.py:260).
+
+    ``cfg_group`` (2 ranks): CFG halves on different GPUs ("C2 at 2 GPUs"): rank 0 of the group
+    evaluates the negative half, rank 1 the positive half, one all-gather of the velocities per step, then both
+    ranks apply the same update.  ``context_input`` / ``mask_input`` / ``t_tensor`` then hold this rank's half."""
     b = latents.shape[0]
+    if do_cfg and cfg_group is not None:
+        import torch.distributed as dist
+        mine = dit_model(latents, context_input, mask_input, t_tensor)
+        both = torch.empty((2,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(both.view(2 * b, *mine.shape[1:]), mine.contiguous(), group=cfg_group)
+        ops.cfg_euler(acc, both[0], both[1], guidance_scale, dt, latents, do_cfg=True)
+        return both.view(2 * b, *mine.shape[1:])
     if do_cfg:
         out = dit_model(torch.cat([latents] * 2), context_input, mask_input, t_tensor)
         uncond, cond = out[:b], out[b:]
@@ -72,7 +83,7 @@ def denoise_step(dit_model, latents, acc, context_input, mask_input, t_tensor, d
 @torch.no_grad()
 def denoise(dit_model, latents, negative_embeds, prompt_embeds, mask=None, num_inference_steps: int = 30,
             guidance_scale: float = 6.0, alpha: Optional[float] = None, acc_dtype=torch.bfloat16,
-            apg_config: Optional[APGConfig] = None, trace: Optional[list] = None):
+            apg_config: Optional[APGConfig] = None, trace: Optional[list] = None, cfg_group=None):
     """The sampling loop of f_lite/pipeline.py:244-297 (acc_dtype=bf16) / f_lite/train.py:573-599
     (acc_dtype=fp32).  ``mask`` covers ``[negative, positive]`` rows (None = all ones)."""
     b = latents.shape[0]
@@ -81,7 +92,13 @@ def denoise(dit_model, latents, negative_embeds, prompt_embeds, mask=None, num_i
     if alpha is None:
         alpha = default_alpha(latents.shape[2], latents.shape[3])
     do_cfg = guidance_scale >= 1.0                                                        # pipeline.py:248
-    if do_cfg:
+    split_cfg = do_cfg and cfg_group is not None
+    if split_cfg:
+        import torch.distributed as dist
+        half = dist.get_rank(cfg_group)                 # 0: negative half, 1: positive half
+        context_input = (negative_embeds, prompt_embeds)[half].contiguous()
+        mask_input = None if mask is None else mask[half * b:(half + 1) * b].contiguous()
+    elif do_cfg:
         context_input = torch.cat([negative_embeds, prompt_embeds])
         mask_input = mask
     else:
@@ -89,7 +106,7 @@ def denoise(dit_model, latents, negative_embeds, prompt_embeds, mask=None, num_i
         mask_input = None if mask is None else mask[b:]
     apg = apg_config is not None and apg_config.enabled
     sched = time_shift_schedule(num_inference_steps, alpha)
-    rows = 2 * b if do_cfg else b
+    rows = 2 * b if (do_cfg and not split_cfg) else b
     # torch.tensor([t] * batch, dtype=model dtype) of pipeline.py:260, for every step, in one H2D copy
     t_all = torch.tensor([[t] * rows for t, _ in sched], dtype=latents.dtype).to(latents.device)
     for step, (t, dt) in enumerate(sched):
@@ -106,7 +123,8 @@ def denoise(dit_model, latents, negative_embeds, prompt_embeds, mask=None, num_i
             v = dy + (guidance_scale - 1) * orth
             ops.cfg_euler(acc, None, v.contiguous(), 1.0, dt, latents, do_cfg=False)
         else:
-            out = denoise_step(dit_model, latents, acc, context_input, mask_input, t_tensor, dt, guidance_scale, do_cfg)
+            out = denoise_step(dit_model, latents, acc, context_input, mask_input, t_tensor, dt, guidance_scale, do_cfg,
+                               cfg_group=cfg_group if split_cfg else None)
         if trace is not None:
             trace.append(out.clone())
     return latents if acc_dtype == torch.bfloat16 else acc

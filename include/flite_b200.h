@@ -88,9 +88,15 @@ int flite_rmsnorm_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, con
 int flite_rope_qknorm(void* buf, int64_t ld, int rows, int n_slots, const void* cos_t, const void* sin_t,
                       int rows_per_sample, float eps, void* stream);
 
-/* Patch embedding + register tokens -> tokens[B*(n_reg + hw), d].                         model.py:318-328,535 */
+/* Patch embedding + register tokens -> tokens[B*tok_count, d].                             model.py:318-328,535
+ *   Rows are (sample, local token) for sequence positions [tok_offset, tok_offset + tok_count) of the
+ *   n_reg + hw tokens (tok_count <= 0: the whole sequence; a slice is what a sequence-parallel rank owns). */
 int flite_patch_embed(const void* x, const void* w, const void* bias, const void* reg_tokens, void* out,
-                      int B, int C, int H, int W, int P, int d, int n_reg, void* stream);
+                      int B, int C, int H, int W, int P, int d, int n_reg, int tok_offset, int tok_count,
+                      void* stream);
+
+/* dst[n1, n0, n2] = src[n0, n1, n2] (bf16, n2 % 8 == 0): layout transform around the Ulysses all-to-alls. */
+int flite_permute_021(const void* src, void* dst, int n0, int n1, int n2, void* stream);
 
 /* Sinusoidal timestep embedding; t is fp32 on device.                                    model.py:20-28,551
  *   t_is_bf16: 0 = fp32 timesteps; 1 = bf16 timesteps (reproduces `timesteps*1000` rounded to bf16);
@@ -114,11 +120,15 @@ int flite_pack_context(const void* src, int64_t lds, void* dst, int64_t ldd, con
  *   EPI_GATED_RES: resid [M, ldr], gate row = gate + (row / rows_per_sample) * ld_gate
  *   EPI_SWIGLU   : C has N/2 columns
  *   EPI_QKV_ROPE : columns [0, qk_cols) are 256-wide heads that get RoPE (rope_cos/sin bf16
- *                  [rows_per_sample, 128], may be NULL) and RMSNorm(eps); the rest is bias only */
+ *                  [rows_per_sample, 128], may be NULL) and RMSNorm(eps); the rest is bias only.
+ *                  sp_ranks > 0 (Ulysses): N = 3*d; head h of q|k|v is written into the all-to-all send layout
+ *                  C[(sample*sp_ranks + h / sp_heads_per_rank)*rows_per_sample + local_row,
+ *                    which*sp_heads_per_rank*256 + (h % sp_heads_per_rank)*256 ...], ldc = 3*sp_heads_per_rank*256 */
 int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N,
                     int K, const void* bias, int act, int epilogue, const void* resid, int64_t ldr,
                     const void* gate, int64_t ld_gate, int rows_per_sample, const void* rope_cos,
-                    const void* rope_sin, int qk_cols, float eps, int variant, void* stream);
+                    const void* rope_sin, int qk_cols, float eps, int sp_ranks, int sp_heads_per_rank, int variant,
+                    void* stream);
 
 /* Varlen non-causal flash attention, head_dim 256.                                        model.py:203-211
  *   q[rows_q, ldq] head h at columns q_col0 + 256 h (same for k, v); cu_q / cu_k int32 [B+1] on device;

@@ -58,11 +58,11 @@ def test_fails_loudly_without_gpu():
 def test_bad_arguments_return_error_codes():
     lib = _lib.load()
     assert lib.flite_gemm_bf16(None, 8, None, 8, None, 8, 1, 64, 64, None, 0, 0, None, 0, None, 0, 0, None, None, 0,
-                               1e-6, 0, None) == -1
+                               1e-6, 0, 0, 0, None) == -1
     assert b"null" in lib.flite_last_error()
     one = ctypes.c_void_p(16)
     assert lib.flite_gemm_bf16(one, 8, one, 8, one, 8, 1, 64, 63, None, 0, 0, None, 0, None, 0, 0, None, None, 0,
-                               1e-6, 0, None) == -1
+                               1e-6, 0, 0, 0, None) == -1
     assert b"K = 63" in lib.flite_last_error()
     assert lib.flite_cfg_euler(one, 0, one, one, 6.0, 0.1, 1, one, 12, None) == -1
 
