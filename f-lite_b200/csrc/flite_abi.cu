@@ -123,7 +123,8 @@ int num_sms() {
 }
 
 template <int kCtaGroup, int BLOCK_N, int kStages, int kEpi>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, GemmParams p,
+                cudaStream_t stream) {
     using S = GemmSmem<kCtaGroup, BLOCK_N, kStages>;
     auto kern = gemm_bf16_kernel<kCtaGroup, BLOCK_N, kStages, kEpi>;
     static bool configured = false;
@@ -133,8 +134,20 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
     }
     const int tile_m = 128 * kCtaGroup;
     const int num_tiles = ((p.M + tile_m - 1) / tile_m) * (p.N / BLOCK_N);
-    int clusters = num_sms() / kCtaGroup;
-    if (clusters > num_tiles) clusters = num_tiles;
+    const int max_clusters = num_sms() / kCtaGroup;
+    // tail balancing: a last partial wave of `tail` tiles is run as 2*tail half-width tiles when that still fits in
+    // one wave (needs 128-column granularity for SwiGLU pairs, whole heads for the QKV epilogue => not there)
+    p.full_units = num_tiles;
+    p.num_units = num_tiles;
+    const bool can_split = kEpi != EPI_QKV_ROPE && (BLOCK_N / 2) % (kEpi == EPI_SWIGLU ? 128 : 32) == 0 &&
+                           (BLOCK_N / 2 / kCtaGroup) >= 8 && g_tuning[FLITE_TUNE_GEMM_TAIL_SPLIT] == 0;
+    const int tail = num_tiles % max_clusters;
+    if (can_split && tail > 0 && 2 * tail <= max_clusters) {
+        p.full_units = num_tiles - tail;
+        p.num_units = p.full_units + 2 * tail;
+    }
+    int clusters = max_clusters;
+    if (clusters > p.num_units) clusters = p.num_units;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * kCtaGroup);
     cfg.blockDim = dim3(GEMM_THREADS);
@@ -147,20 +160,21 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbh, p));
     return 0;
 }
 
 template <int kCtaGroup, int BLOCK_N, int kStages>
-int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const GemmParams& p,
+                 cudaStream_t s) {
     switch (epi) {
-        case EPI_STORE: return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_STORE>(ta, tb, p, s);
-        case EPI_GATED_RES: return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_GATED_RES>(ta, tb, p, s);
+        case EPI_STORE: return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_STORE>(ta, tb, tbh, p, s);
+        case EPI_GATED_RES: return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_GATED_RES>(ta, tb, tbh, p, s);
         case EPI_SWIGLU:
-            if constexpr (BLOCK_N % 128 == 0) return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_SWIGLU>(ta, tb, p, s);
+            if constexpr (BLOCK_N % 128 == 0) return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_SWIGLU>(ta, tb, tbh, p, s);
             break;
         case EPI_QKV_ROPE:
-            if constexpr (BLOCK_N == 256) return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_QKV_ROPE>(ta, tb, p, s);
+            if constexpr (BLOCK_N == 256) return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_QKV_ROPE>(ta, tb, tbh, p, s);
             break;
     }
     return fail(FLITE_ERR_INVALID, "epilogue %d not available for N-tile %d", epi, BLOCK_N);
@@ -371,17 +385,19 @@ int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
     p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin; p.qk_cols = qk_cols; p.eps = eps;
     p.sp_ranks = sp_ranks; p.sp_hp = sp_heads_per_rank; p.n_heads = N / 768;
 
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tbh;
     int rc = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128);
     if (rc) return rc;
     rc = make_tmap(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(block_n / cg));
     if (rc) return rc;
+    rc = make_tmap(&tbh, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(block_n / cg / 2));   // half-width tail tiles
+    if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     switch (variant) {
-        case FLITE_GEMM_1CTA_N256: return dispatch_epi<1, 256, 4>(epilogue, ta, tb, p, s);
-        case FLITE_GEMM_2CTA_N256: return dispatch_epi<2, 256, 6>(epilogue, ta, tb, p, s);
-        case FLITE_GEMM_1CTA_N128: return dispatch_epi<1, 128, 6>(epilogue, ta, tb, p, s);
-        case FLITE_GEMM_1CTA_N64: return dispatch_epi<1, 64, 8>(epilogue, ta, tb, p, s);
+        case FLITE_GEMM_1CTA_N256: return dispatch_epi<1, 256, 4>(epilogue, ta, tb, tbh, p, s);
+        case FLITE_GEMM_2CTA_N256: return dispatch_epi<2, 256, 6>(epilogue, ta, tb, tbh, p, s);
+        case FLITE_GEMM_1CTA_N128: return dispatch_epi<1, 128, 6>(epilogue, ta, tb, tbh, p, s);
+        case FLITE_GEMM_1CTA_N64: return dispatch_epi<1, 64, 8>(epilogue, ta, tb, tbh, p, s);
     }
     return fail(FLITE_ERR_INVALID, "gemm: unreachable");
 }

@@ -43,6 +43,10 @@ struct GemmParams {
     int sp_ranks;
     int sp_hp;                   // heads per rank
     int n_heads;
+    // Tail balancing: work units [0, full_units) are whole tiles; units beyond are HALF tiles (BLOCK_N/2 columns)
+    // of the remaining tiles, so that a last partial wave is spread over twice as many clusters.
+    int full_units;              // == number of tiles when no split is used
+    int num_units;
 };
 
 constexpr int GEMM_BLOCK_K = 64;
@@ -61,7 +65,7 @@ struct GemmSmem {
 template <int kCtaGroup, int BLOCK_N, int kStages, int kEpi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_b_half, const GemmParams p) {
     using S = GemmSmem<kCtaGroup, BLOCK_N, kStages>;
     constexpr int TILE_M = 128 * kCtaGroup;
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
@@ -108,6 +112,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int num_m_tiles = (p.M + TILE_M - 1) / TILE_M;
     const int num_n_tiles = p.N / BLOCK_N;
     const int num_tiles = num_m_tiles * num_n_tiles;
+    (void)num_tiles;
+    // unit -> (tile, half): half == -1 means the whole tile, 0/1 the left/right BLOCK_N/2 columns
+    auto unit_tile = [&](int u, int& tile, int& half) {
+        if (u < p.full_units) { tile = u; half = -1; }
+        else { tile = p.full_units + ((u - p.full_units) >> 1); half = (u - p.full_units) & 1; }
+    };
     const int num_kb = p.K / GEMM_BLOCK_K;
     const int cluster_id = blockIdx.x / kCtaGroup;
     const int num_clusters = gridDim.x / kCtaGroup;
@@ -117,21 +127,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int unit = cluster_id; unit < p.num_units; unit += num_clusters) {
+                int tile, half;
+                unit_tile(unit, tile, half);
+                const int bn_cta = (half < 0) ? S::BN_CTA : S::BN_CTA / 2;       // W rows this CTA stages
                 const int m0 = (tile % num_m_tiles) * TILE_M + (int)cta_rank * 128;
-                const int n0 = (tile / num_m_tiles) * BLOCK_N + (int)cta_rank * S::BN_CTA;
+                const int n0 = (tile / num_m_tiles) * BLOCK_N + (half > 0 ? BLOCK_N / 2 : 0) + (int)cta_rank * bn_cta;
+                const CUtensorMap* tb = (half < 0) ? &tmap_b : &tmap_b_half;
+                const uint32_t stage_bytes = S::A_BYTES + bn_cta * GEMM_BLOCK_K * 2;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait<kCtaGroup == 2>(&empty_bar[stage], phase ^ 1, 1);
                     uint8_t* sa = smem + stage * S::STAGE_BYTES;
                     uint8_t* sb = sa + S::A_BYTES;
                     if constexpr (kCtaGroup == 1) {
-                        mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                         tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+                        tma_load_2d(sb, tb, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
                     } else {
-                        if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+                        if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
                         tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], 0, kb * GEMM_BLOCK_K, m0);
-                        tma_load_2d_cg2(sb, &tmap_b, &full_bar[stage], 0, kb * GEMM_BLOCK_K, n0);
+                        tma_load_2d_cg2(sb, tb, &full_bar[stage], 0, kb * GEMM_BLOCK_K, n0);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -141,11 +156,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp_idx == 1) {
         // ================================ MMA issuer ================================
         if (is_leader && elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
+            constexpr uint32_t idesc_full = make_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
+            constexpr uint32_t idesc_half = make_idesc_bf16(TILE_M, BLOCK_N / 2, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+            for (int unit = cluster_id; unit < p.num_units; unit += num_clusters, ++it) {
+                const uint32_t idesc = (unit < p.full_units) ? idesc_full : idesc_half;
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait<kCtaGroup == 2>(&tmem_empty_bar[acc], acc_phase ^ 1, 2);
@@ -177,11 +194,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
         const int lane = (int)lane_id();
         int it = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        for (int unit = cluster_id; unit < p.num_units; unit += num_clusters, ++it) {
+            int tile, half;
+            unit_tile(unit, tile, half);
+            const int bn_eff = (half < 0) ? BLOCK_N : BLOCK_N / 2;     // accumulator columns of this unit
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (tile % num_m_tiles) * TILE_M + (int)cta_rank * 128;
-            const int n0 = (tile / num_m_tiles) * BLOCK_N;
+            const int n0 = (tile / num_m_tiles) * BLOCK_N + (half > 0 ? BLOCK_N / 2 : 0);
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
             mbar_wait<kCtaGroup == 2>(&tmem_full_bar[acc], acc_phase, 4);
@@ -193,7 +213,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if constexpr (kEpi == EPI_GATED_RES)
                     gate_row = p.gate + (long long)((row_ok ? row : 0) / p.rows_per_sample) * p.ld_gate;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                for (int c = 0; c < bn_eff / 32; ++c) {
                     uint32_t r[32];
                     tmem_ld_x32(taddr + c * 32, r);
                     tmem_ld_wait();
@@ -256,11 +276,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 // weight rows are interleaved in groups of 64: [gate 64 | up 64] per 128 accumulator columns
                 static_assert(kEpi != EPI_SWIGLU || BLOCK_N % 128 == 0, "SwiGLU epilogue needs 128-column groups");
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 64; ++c) {
-                    const int grp = c >> 1, half = c & 1;
+                for (int c = 0; c < bn_eff / 64; ++c) {
+                    const int grp = c >> 1, hf = c & 1;
                     uint32_t g[32], u[32];
-                    tmem_ld_x32(taddr + grp * 128 + half * 32, g);
-                    tmem_ld_x32(taddr + grp * 128 + 64 + half * 32, u);
+                    tmem_ld_x32(taddr + grp * 128 + hf * 32, g);
+                    tmem_ld_x32(taddr + grp * 128 + 64 + hf * 32, u);
                     tmem_ld_wait();
                     uint32_t outp[16];
 #pragma unroll
@@ -273,7 +293,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         outp[j] = pack_bf16x2(g0 * u0, g1 * u1);
                     }
                     if (row_ok) {
-                        const int col = n0 / 2 + grp * 64 + half * 32;
+                        const int col = n0 / 2 + grp * 64 + hf * 32;
                         uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + col);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)

@@ -58,6 +58,7 @@ extern "C" {
 #define FLITE_TUNE_ATTN_VARIANT 1    /* default attention variant when the call passes FLITE_ATTN_AUTO */
 #define FLITE_TUNE_GEMM_VARIANT 2    /* default GEMM variant when the call passes FLITE_GEMM_AUTO (0 = heuristic) */
 #define FLITE_TUNE_ATTN_DEBUG 3      /* profiling experiments only: bit0 skip softmax math, bit1 skip K/V reloads */
+#define FLITE_TUNE_GEMM_TAIL_SPLIT 4 /* 0 = run a last partial wave as half-width tiles (default), 1 = off */
 int flite_set_tuning(int key, int value);
 
 int flite_abi_version(void);
