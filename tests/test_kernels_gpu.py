@@ -263,3 +263,40 @@ def test_pack_context_matches_nonzero_index_select():
     assert torch.equal(packed[: idx.numel()], ctx.reshape(-1, d)[idx])
     assert packed[idx.numel():].abs().max().item() == 0
     assert cu.tolist() == [0] + mask.sum(1).cumsum(0).int().tolist()                        # model.py:50-56
+
+
+# ----------------------------------------------------------------------------- sequence-parallel plumbing kernels
+@pytest.mark.parametrize("P", [2, 4])
+def test_qkv_epilogue_head_scatter_matches_all_to_all_layout(P):
+    """Ulysses: the QKV epilogue writes [sample][dest rank][local token][q|k|v][head % Hp][256] directly."""
+    from flite_b200 import ops
+    B, Lq, H = 2, 136, 4
+    d, Hp = H * 256, H // P
+    dq = d // P
+    M = B * Lq
+    a, w, b = rnd(M, d, scale=0.5, seed=1), rnd(3 * d, d, scale=0.05, seed=2), rnd(3 * d, seed=3)
+    ang = torch.rand(Lq, 128, device=DEV) * 6.28
+    cos, sin = ang.cos().bfloat16(), ang.sin().bfloat16()
+    plain = ops.gemm(a, w, b, epilogue=ops.EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin, qk_cols=2 * d, rows_per_sample=Lq)
+    send = torch.zeros(B * P * Lq, 3 * dq, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, w, b, epilogue=ops.EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin, qk_cols=2 * d, rows_per_sample=Lq,
+             out=send, sp_ranks=P, sp_heads_per_rank=Hp)
+    # reference layout: plain [B, Lq, 3, P, Hp*256] -> [B, P, Lq, 3, Hp*256]
+    ref = plain.view(B, Lq, 3, P, dq).permute(0, 3, 1, 2, 4).reshape(B * P * Lq, 3 * dq)
+    assert torch.equal(send, ref)
+
+
+def test_patch_embed_token_slice_and_permute():
+    from flite_b200 import ops
+    B, C, H, W, P, d = 2, 16, 32, 64, 2, 512
+    x = rnd(B, C, H, W, seed=1)
+    w, b, reg = rnd(d, C, P, P, scale=0.1, seed=2), rnd(d, seed=3), rnd(1, 16, d, seed=4)
+    L = 16 + (H // P) * (W // P)
+    full = ops.patch_embed(x, w, b, reg, P).view(B, L, d)
+    for ranks in (2, 4):
+        Lq = L // ranks
+        for r in range(ranks):
+            part = ops.patch_embed(x, w, b, reg, P, tok_offset=r * Lq, tok_count=Lq).view(B, Lq, d)
+            assert torch.equal(part, full[:, r * Lq:(r + 1) * Lq])
+    t = rnd(3, 5, 64, seed=5)
+    assert torch.equal(ops.permute_021(t), t.permute(1, 0, 2).contiguous())
