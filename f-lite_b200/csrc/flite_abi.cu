@@ -12,6 +12,7 @@
 
 #include "../../include/flite_b200.h"
 #include "attn_cg2_sm100.cuh"
+#include "attn_qtmem_sm100.cuh"
 #include "attn_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
@@ -418,19 +419,15 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_cg2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_cg2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_cg2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_qtmem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(attn_fwd_qtmem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM));
         configured = true;
     }
-    if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_2CTA_2WG_PTMEM)
+    if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_QTMEM_2WG)
         return fail(FLITE_ERR_INVALID, "attention: unknown variant %d", variant);
     if (variant == FLITE_ATTN_AUTO) variant = g_tuning[FLITE_TUNE_ATTN_VARIANT] ? g_tuning[FLITE_TUNE_ATTN_VARIANT] : FLITE_ATTN_2CTA_1WG_PTMEM;
-    const bool cg2 = variant >= FLITE_ATTN_2CTA_1WG;
-    CUtensorMap tq, tk, tv;
-    int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)ldq, (uint64_t)ldq, 128);
-    if (rc) return rc;
-    rc = make_tmap(&tk, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldk, (uint64_t)ldk, cg2 ? 64 : 128);
-    if (rc) return rc;
-    rc = make_tmap(&tv, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldv, (uint64_t)ldv, 128);
-    if (rc) return rc;
+    const bool cg2 = variant >= FLITE_ATTN_2CTA_1WG && variant <= FLITE_ATTN_2CTA_2WG_PTMEM;
+    const bool qtmem = variant == FLITE_ATTN_QTMEM_1WG || variant == FLITE_ATTN_QTMEM_2WG;
     AttnParams p;
     p.cu_q = cu_q; p.cu_k = cu_k;
     p.out = (__nv_bfloat16*)out; p.ldo = ldo;
@@ -438,6 +435,37 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     p.debug = g_tuning[FLITE_TUNE_ATTN_DEBUG];
     const int q_tiles = (max_q + 127) / 128;
+    if (qtmem) {
+        CUtensorMap tk2, tv2;
+        int rc2 = make_tmap(&tk2, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldk, (uint64_t)ldk, 32);
+        if (rc2) return rc2;
+        rc2 = make_tmap(&tv2, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldv, (uint64_t)ldv, 64);
+        if (rc2) return rc2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * ((q_tiles + 1) / 2), H, B);
+        cfg.blockDim = dim3(variant == FLITE_ATTN_QTMEM_1WG ? 192 : 320);
+        cfg.dynamicSmemBytes = AQ_SMEM;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const __nv_bfloat16* qp = (const __nv_bfloat16*)q;
+        long long ldq_ = ldq;
+        if (variant == FLITE_ATTN_QTMEM_1WG) CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_qtmem_kernel<1>, tk2, tv2, qp, ldq_, p));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_qtmem_kernel<2>, tk2, tv2, qp, ldq_, p));
+        return 0;
+    }
+    CUtensorMap tq, tk, tv;
+    int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)ldq, (uint64_t)ldq, 128);
+    if (rc) return rc;
+    rc = make_tmap(&tk, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldk, (uint64_t)ldk, cg2 ? 64 : 128);
+    if (rc) return rc;
+    rc = make_tmap(&tv, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldv, (uint64_t)ldv, 128);
+    if (rc) return rc;
     if (!cg2) {
         dim3 grid(q_tiles, H, B);
         if (variant == FLITE_ATTN_1WG) attn_fwd_kernel<1><<<grid, 192, ATT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);

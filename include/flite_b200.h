@@ -52,6 +52,8 @@ extern "C" {
 #define FLITE_ATTN_2CTA_2WG 4 /* same with two softmax warpgroups                                           */
 #define FLITE_ATTN_2CTA_1WG_PTMEM 5 /* cta_group::2, P kept in TMEM (A operand of the PV MMA read from TMEM); default */
 #define FLITE_ATTN_2CTA_2WG_PTMEM 6
+#define FLITE_ATTN_QTMEM_1WG 7 /* cta_group::2, Q and P both TMEM operands, 64-key tiles, 6-stage K/V ring */
+#define FLITE_ATTN_QTMEM_2WG 8
 
 /* tuning knobs (A/B switches used by the benchmarks; defaults are the measured best) */
 #define FLITE_TUNE_RMSNORM_KERNEL 0  /* 0 auto | 1 two-pass | 2 register-resident */

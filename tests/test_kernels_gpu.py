@@ -164,7 +164,7 @@ ATT_CASES = [(1, 1, 128, 128), (1, 2, 256, 384), (2, 2, 272, 272), (2, 2, 272, 1
              (2, 12, 4112, 256)]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("B,H,Lq,Lk", ATT_CASES)
 def test_attention_uniform(B, H, Lq, Lk, variant):
     from flite_b200 import ops
@@ -180,7 +180,7 @@ def test_attention_uniform(B, H, Lq, Lk, variant):
     assert rel(out, ref.reshape(-1, d)) <= 5e-3          # bf16 output + bf16 P, same as FA2's own error
 
 
-@pytest.mark.parametrize("variant", [1, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 3, 4, 5, 6, 7, 8])
 def test_attention_ragged_and_empty_keys(variant):
     from flite_b200 import ops
     from oracle.dit_oracle import flash_attn_varlen
