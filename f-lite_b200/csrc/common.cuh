@@ -85,7 +85,10 @@ FLITE_DEVICE void mbar_arrive(uint64_t* bar) {
 // arrive on the barrier at the same smem offset in CTA `rank` of the cluster
 FLITE_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
     uint32_t remote = mapa_shared(smem_u32(bar), rank);
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    // default semantics (release.cta), as CUTLASS's ClusterBarrier::arrive(cta_id): a .release.cluster here compiles to
+    // MEMBAR.ALL.GPU + ERRBAR (measured: 21 % of the softmax warps' stall samples).  The data these arrivals publish
+    // lives in TMEM / is fenced with fence.proxy.async, ordered by tcgen05.fence::before_thread_sync.
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
 FLITE_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -113,7 +116,8 @@ FLITE_DEVICE bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        // default (acquire.cta) like CUTLASS's ClusterBarrier::wait: acquire.cluster adds a CCTL.IVALL (L1 invalidate)
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, P1;\n\t"
         "}\n"
         : "=r"(ok)

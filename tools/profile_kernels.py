@@ -26,8 +26,9 @@ if which in ("attn", "all"):
     qkv = torch.randn(T, 3 * d, device=dev).bfloat16()
     cu = torch.arange(3, device=dev, dtype=torch.int32) * (T // 2)
     o = torch.empty(T, d, device=dev, dtype=torch.bfloat16)
+    var = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     for _ in range(6):
-        ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, 12, T // 2, 256 ** -0.5, out=o)
+        ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, 12, T // 2, 256 ** -0.5, out=o, variant=var)
 if which in ("norm", "all"):
     x = torch.randn(T, d, device=dev).bfloat16(); w = torch.ones(d, device=dev).bfloat16()
     mod = torch.randn(2, 9 * d, device=dev).bfloat16(); y = torch.empty_like(x)
