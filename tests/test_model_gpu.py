@@ -175,3 +175,30 @@ def test_full_size_c2_velocity_parity():
         assert v_or.float().std().item() > 0.1 and r <= TOL
     del m, sd
     torch.cuda.empty_cache()
+
+
+def test_decoded_image_psnr_vs_reference_trajectory(golden_dir):
+    """north_star image criterion: final decoded image PSNR >= 40 dB against the reference image.  Config C1 (tiny DiT,
+    256x256, 4 Euler steps, CFG 6): the new path's trajectory and the reference bf16 trajectory (oracle) are decoded by the
+    SAME FLUX-style decoder (random init, oracle/vae_decoder.py) and post-processed like f_lite/pipeline.py:324-326."""
+    import flite_b200
+    from oracle import dit_oracle, sampler_oracle, vae_decoder
+    from oracle.make_golden import build_case
+    g = torch.load(os.path.join(golden_dir, "tiny_256_sampler.pt"), weights_only=False)
+    rec = g["recipe"]
+    sd, x, ctx, mask, _ = build_case(rec, device=DEV)
+    b = rec["batch"]
+    m = _model(rec["cfg"], sd)
+    lat = flite_b200.denoise(m, x[:b].bfloat16(), ctx[:b].bfloat16(), ctx[b:].bfloat16(), mask, g["steps"], g["guidance"])
+    sdb = {k: w.bfloat16() for k, w in sd.items()}
+    fn = lambda *a: dit_oracle.dit_forward(sdb, rec["cfg"], *a)
+    olat = sampler_oracle.sample_pipeline(fn, x[:b].bfloat16(), ctx[:b].bfloat16(), ctx[b:].bfloat16(), mask.bfloat16(),
+                                          g["steps"], g["guidance"])
+    dec = vae_decoder.make_decoder(0, DEV)
+    img, ref = vae_decoder.decode_to_image(dec, lat), vae_decoder.decode_to_image(dec, olat)
+    ref32 = vae_decoder.decode_to_image(dec, g["latents_pipeline"].to(DEV))          # fp32 reference trajectory (CPU fixture)
+    p = vae_decoder.psnr(img, ref)
+    print(f"PSNR vs reference bf16 image {p:.1f} dB | vs fp32 reference image: mine {vae_decoder.psnr(img, ref32):.1f} dB, "
+          f"reference-bf16 {vae_decoder.psnr(ref, ref32):.1f} dB | image std {ref.std().item():.2f}")
+    assert ref.std().item() > 0.1           # the decoded image is not flat
+    assert p >= 40.0
