@@ -35,10 +35,14 @@ UNIT = "steps/s"
 ARCH_10B = dict(in_channels=16, patch_size=2, hidden_size=3072, depth=40, num_heads=12, mlp_ratio=4.0,
                 cross_attn_input_size=4096, train_bias_and_rms=True, use_rope=True)
 ARCH_TINY = dict(ARCH_10B, hidden_size=512, depth=4, num_heads=2)
+ARCH_7B = dict(ARCH_10B, depth=28)     # ASSUMED: "7B" is not defined anywhere in the reference
 WORKLOADS = {
-    # name: (arch, height, width, ctx_len, images per GPU)
+    # name: (arch, height, width, ctx_len, images per GPU)   -- BASELINE.json configs[0..4]
     "c2": (ARCH_10B, 1024, 1024, 256, 1),
     "c1": (ARCH_TINY, 256, 256, 256, 1),
+    "c3": (ARCH_7B, 1344, 896, 256, 8),     # 64 prompts over 8 GPUs = 8 images (16 CFG sequences) per GPU
+    "c4": (ARCH_10B, 2048, 2048, 256, 1),   # single 2048^2 image (1-GPU form; Ulysses form: tools/mgpu_check.py)
+    "c5": (ARCH_10B, 1024, 1024, 256, 4),   # batch 32 over 8 GPUs = 4 images per GPU (VAE decode not included)
 }
 
 
@@ -365,7 +369,7 @@ def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
                    "parallelism": f"dp{world} (one image per GPU, no data-path collective)",
                    "weights": "random-init, de-zeroed (seed 0), replicated per GPU",
                    "context_kv": "recomputed every step (hoisting disabled)",
-                   "l2": "13.7 GB of weights streamed per step >> 126 MB L2, no flush needed",
+                   "l2": "GBs of weights streamed per step >> 126 MB L2, no flush needed",
                    "flops_per_step_per_gpu": fl},
         "tflops_per_gpu": fl / (ms_step * 1e-3) / 1e12,
         "tensor_frac_of_burst_peak": fl / (ms_step * 1e-3) / 1e12 / peaks["bf16"],
@@ -375,7 +379,7 @@ def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
                 "d2h_bytes_per_step": d2h, "api": "flite_b200.denoise_step (DiT.forward + flite_cfg_euler) on host buffers"},
         "gpu_launches": launches, "clocks": clk, "roofline": roof,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload in ("c1", "c2"):
         steps, cores, sample = cpu_reference_sample(cfg, height, width, ctx_len, images, repeats=1)
         line["cpu_baseline"] = {"value": 1.0 / steps[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
