@@ -147,6 +147,16 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         p.full_units = num_tiles - tail;
         p.num_units = p.full_units + 2 * tail;
     }
+    // band height: keep a band of A within ~32 MB of L2 (A tile = tile_m x K bf16); small problems use one band
+    {
+        const int num_m_tiles = (p.M + tile_m - 1) / tile_m;
+        const long long a_tile_bytes = (long long)tile_m * p.K * 2;
+        long long g = (32ll << 20) / a_tile_bytes;
+        if (g < 1) g = 1;
+        if (g > 16) g = 16;
+        if ((long long)num_m_tiles * a_tile_bytes <= (48ll << 20) || g_tuning[FLITE_TUNE_GEMM_BAND] == 1) g = num_m_tiles;
+        p.band_m = (int)g;
+    }
     int clusters = max_clusters;
     if (clusters > p.num_units) clusters = p.num_units;
     cudaLaunchConfig_t cfg = {};

@@ -47,6 +47,9 @@ struct GemmParams {
     // of the remaining tiles, so that a last partial wave is spread over twice as many clusters.
     int full_units;              // == number of tiles when no split is used
     int num_units;
+    // Rasterisation: tiles are ordered band by band (band_m consecutive M-tiles), N-tile by N-tile inside a band and
+    // M fastest, so that a band of A (band_m x TILE_M x K) stays L2-resident while W streams past it once per band.
+    int band_m;
 };
 
 constexpr int GEMM_BLOCK_K = 64;
@@ -113,6 +116,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int num_n_tiles = p.N / BLOCK_N;
     const int num_tiles = num_m_tiles * num_n_tiles;
     (void)num_tiles;
+    auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+        const int per_band = p.band_m * num_n_tiles;
+        const int band = tile / per_band, rem = tile - band * per_band;
+        const int m_first = band * p.band_m;
+        const int gm = min(p.band_m, num_m_tiles - m_first);
+        m_blk = m_first + rem % gm;
+        n_blk = rem / gm;
+    };
     // unit -> (tile, half): half == -1 means the whole tile, 0/1 the left/right BLOCK_N/2 columns
     auto unit_tile = [&](int u, int& tile, int& half) {
         if (u < p.full_units) { tile = u; half = -1; }
@@ -131,8 +142,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 int tile, half;
                 unit_tile(unit, tile, half);
                 const int bn_cta = (half < 0) ? S::BN_CTA : S::BN_CTA / 2;       // W rows this CTA stages
-                const int m0 = (tile % num_m_tiles) * TILE_M + (int)cta_rank * 128;
-                const int n0 = (tile / num_m_tiles) * BLOCK_N + (half > 0 ? BLOCK_N / 2 : 0) + (int)cta_rank * bn_cta;
+                int m_blk, n_blk;
+                tile_coords(tile, m_blk, n_blk);
+                const int m0 = m_blk * TILE_M + (int)cta_rank * 128;
+                const int n0 = n_blk * BLOCK_N + (half > 0 ? BLOCK_N / 2 : 0) + (int)cta_rank * bn_cta;
                 const CUtensorMap* tb = (half < 0) ? &tmap_b : &tmap_b_half;
                 const uint32_t stage_bytes = S::A_BYTES + bn_cta * GEMM_BLOCK_K * 2;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -200,8 +213,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int bn_eff = (half < 0) ? BLOCK_N : BLOCK_N / 2;     // accumulator columns of this unit
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (tile % num_m_tiles) * TILE_M + (int)cta_rank * 128;
-            const int n0 = (tile / num_m_tiles) * BLOCK_N + (half > 0 ? BLOCK_N / 2 : 0);
+            int m_blk, n_blk;
+            tile_coords(tile, m_blk, n_blk);
+            const int m0 = m_blk * TILE_M + (int)cta_rank * 128;
+            const int n0 = n_blk * BLOCK_N + (half > 0 ? BLOCK_N / 2 : 0);
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
             mbar_wait<kCtaGroup == 2>(&tmem_full_bar[acc], acc_phase, 4);

@@ -87,7 +87,7 @@ def test_rmsnorm_modulate(rows, d, B, mode):
 
 # ----------------------------------------------------------------------------- GEMM
 GEMM_SHAPES = [(128, 128, 64), (1, 128, 64), (2, 9216, 512), (200, 64, 512), (256, 512, 512), (333, 768, 192),
-               (2 * 272, 1536, 512), (2 * 4112, 3072, 3072)]
+               (2 * 272, 1536, 512), (2 * 4112, 3072, 3072), (16 * 1181, 768, 4096)]   # last: multi-band rasterisation
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
