@@ -147,14 +147,23 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         p.full_units = num_tiles - tail;
         p.num_units = p.full_units + 2 * tail;
     }
-    // band height: keep a band of A within ~32 MB of L2 (A tile = tile_m x K bf16); small problems use one band
+    // Band height (measured on B200, profiles/r1_gemm_band_sweep.json): when A and W together fit in L2 the order does
+    // not matter (single band); when W alone fits (<= 96 MB) thin bands keep W resident while A streams once; otherwise
+    // a band of A of ~32 MB stays resident while W streams past it once per band.
     {
         const int num_m_tiles = (p.M + tile_m - 1) / tile_m;
         const long long a_tile_bytes = (long long)tile_m * p.K * 2;
-        long long g = (32ll << 20) / a_tile_bytes;
-        if (g < 1) g = 1;
-        if (g > 16) g = 16;
-        if ((long long)num_m_tiles * a_tile_bytes <= (48ll << 20) || g_tuning[FLITE_TUNE_GEMM_BAND] == 1) g = num_m_tiles;
+        const long long a_bytes = (long long)num_m_tiles * a_tile_bytes, w_bytes = (long long)p.N * p.K * 2;
+        long long g;
+        if (a_bytes + w_bytes <= (100ll << 20) || g_tuning[FLITE_TUNE_GEMM_BAND] == 1) g = num_m_tiles;
+        else if (g_tuning[FLITE_TUNE_GEMM_BAND] > 1) g = g_tuning[FLITE_TUNE_GEMM_BAND];   // explicit band height (tuning)
+        else if (w_bytes <= (96ll << 20)) g = 2;
+        else {
+            g = (32ll << 20) / a_tile_bytes;
+            if (g < 1) g = 1;
+            if (g > 16) g = 16;
+        }
+        if (g > num_m_tiles) g = num_m_tiles;
         p.band_m = (int)g;
     }
     int clusters = max_clusters;
