@@ -36,6 +36,16 @@ SIGNATURES = {
     "flite_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _I, _I, _P, _L, _P, _L, _I, _P, _P, _I, _F,
                         _I, _I, _I, _P],
     "flite_attention_varlen": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _I, _F, _I, _P],
+    "flite_gemm_qkv_p2p": [_P, _L, _P, _L, _I, _I, _P, _I, _P, _P, _F, _I, _I, _I, _I, _P, _I, _P],
+    "flite_attention_varlen_p2p": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _I, _I, _I, _L, _P, _P, _I, _I, _I,
+                                   _F, _I, _P],
+    "flite_p2p_alloc": [_L, _P],
+    "flite_p2p_free": [_P],
+    "flite_ipc_get_handle": [_P, _P],
+    "flite_ipc_open": [_P, _P],
+    "flite_ipc_close": [_P],
+    "flite_p2p_signal": [_P, _I, _I, ctypes.c_uint, _P],
+    "flite_p2p_wait": [_P, _I, ctypes.c_uint, _P],
 }
 
 _lib = None

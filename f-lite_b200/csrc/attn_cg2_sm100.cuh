@@ -276,6 +276,10 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int row_in_seq = qt * 128 + r;
         const bool row_ok = row_in_seq < q_len;
         __nv_bfloat16* orow = p.out + (long long)(q_beg + row_in_seq) * p.ldo + h * 256 + half * OC;
+        if (p.out_peer[0] != nullptr && row_ok) {   // fused all-to-all: write to the rank that owns this token
+            const int owner = row_in_seq / p.sp_lq, li = row_in_seq - owner * p.sp_lq;
+            orow = p.out_peer[owner] + ((long long)b * p.sp_lq + li) * p.ldo + (p.sp_head0 + h) * 256 + half * OC;
+        }
         if (n_tiles > 0) {
             if constexpr (kWG == 2) {
                 // the parity slot of the (non-existent) next tile is free: tile n-2's reads all precede barrier n-1

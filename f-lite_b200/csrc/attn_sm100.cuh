@@ -29,6 +29,11 @@ struct AttnParams {
     int q_col0, k_col0, v_col0;
     float scale_log2;       // softmax_scale * log2(e)
     int debug;              // profiling experiments only (0 in production): bit0 skip softmax math, bit1 skip K/V reloads
+    // Fused Ulysses return path (attn_fwd_cg2_kernel): when out_peer[0] != nullptr query row l of this rank's heads is
+    // stored into the token owner's buffer over NVLink peer memory: out_peer[l / sp_lq][(b*sp_lq + l % sp_lq), sp_head0 + h]
+    __nv_bfloat16* out_peer[8];
+    int sp_lq;
+    int sp_head0;
 };
 
 constexpr int ATT_SQ = 0, ATT_SK = 65536, ATT_SV = 131072, ATT_SP = 196608, ATT_BAR = 229376;

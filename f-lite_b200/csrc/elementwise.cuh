@@ -337,6 +337,37 @@ permute_021_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n
 }
 
 // ------------------------------------------------------------------------------------------
+// Cross-GPU completion flags for the fused (peer-memory) Ulysses exchange.  signal: after all prior work of this
+// stream (kernel boundary) publish `value` into slot `my_slot` of every peer's flag array; wait: spin until every
+// slot of the local flag array has reached `value` (monotonic epochs, never reset).  One warp, bounded spin.
+// ------------------------------------------------------------------------------------------
+struct PeerFlagPtrs { unsigned int* p[8]; };
+__global__ void p2p_signal_kernel(PeerFlagPtrs peers, int n, int my_slot, unsigned int value) {
+    const int g = threadIdx.x;
+    if (g < n) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.p[g] + my_slot), "r"(value) : "memory");
+    }
+}
+__global__ void p2p_wait_kernel(const unsigned int* flags, int n, unsigned int value) {
+    const int s = threadIdx.x;
+    if (s < n) {
+        const uint64_t t0 = globaltimer_ns();
+        unsigned int v;
+        while (true) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + s) : "memory");
+            if ((int)(v - value) >= 0) break;
+            if (*(volatile unsigned int*)&g_flite_abort != 0) break;
+            if (globaltimer_ns() - t0 > 5000000000ull) {
+                atomicCAS(&g_flite_abort, 0u, (77u << 16) | (unsigned)s | 0x80000000u);
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+// ------------------------------------------------------------------------------------------
 // Sampler: fused CFG combine + Euler update (f_lite/pipeline.py:290,296-297; f_lite/train.py:596,599).
 //   v   = bf16(u + bf16(g * bf16(c - u)))                     (tensor ops in the model dtype)
 //   acc = acc + dt * v      bf16 accumulate (pipeline)  |  fp32 accumulate (train.py sample_images)

@@ -356,10 +356,16 @@ int flite_pack_context(const void* src, int64_t lds, void* dst, int64_t ldd, con
     return 0;
 }
 
-int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
-                    const void* bias, int act, int epilogue, const void* resid, int64_t ldr, const void* gate,
-                    int64_t ld_gate, int rows_per_sample, const void* rope_cos, const void* rope_sin, int qk_cols,
-                    float eps, int sp_ranks, int sp_heads_per_rank, int variant, void* stream) {
+struct SpPeers {
+    void* const* ptrs;
+    int rank;
+    int seq_len;
+};
+
+static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                     const void* bias, int act, int epilogue, const void* resid, int64_t ldr, const void* gate,
+                     int64_t ld_gate, int rows_per_sample, const void* rope_cos, const void* rope_sin, int qk_cols,
+                     float eps, int sp_ranks, int sp_heads_per_rank, int variant, void* stream, const SpPeers* peers) {
     if (!A || !W || !C) return fail(FLITE_ERR_INVALID, "gemm: null pointer");
     if (M <= 0) return 0;
     if (K <= 0 || K % 64) return fail(FLITE_ERR_INVALID, "gemm: K = %d must be a positive multiple of 64", K);
@@ -404,6 +410,15 @@ int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
     p.rows_per_sample = rows_per_sample;
     p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin; p.qk_cols = qk_cols; p.eps = eps;
     p.sp_ranks = sp_ranks; p.sp_hp = sp_heads_per_rank; p.n_heads = N / 768;
+    if (peers) {
+        if (sp_ranks <= 0 || sp_ranks > 8) return fail(FLITE_ERR_INVALID, "gemm: peer scatter needs 1..8 sequence-parallel ranks");
+        for (int i = 0; i < sp_ranks; ++i) {
+            if (!peers->ptrs[i]) return fail(FLITE_ERR_INVALID, "gemm: null peer buffer %d", i);
+            p.sp_peer[i] = (__nv_bfloat16*)peers->ptrs[i];
+        }
+        p.sp_rank = peers->rank;
+        p.sp_seq = peers->seq_len;
+    }
 
     CUtensorMap ta, tb, tbh;
     int rc = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128);
@@ -422,10 +437,38 @@ int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
     return fail(FLITE_ERR_INVALID, "gemm: unreachable");
 }
 
-int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
-                           int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
-                           const int* cu_q, const int* cu_k, int B, int H, int max_q, float softmax_scale,
-                           int variant, void* stream) {
+int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                    const void* bias, int act, int epilogue, const void* resid, int64_t ldr, const void* gate,
+                    int64_t ld_gate, int rows_per_sample, const void* rope_cos, const void* rope_sin, int qk_cols,
+                    float eps, int sp_ranks, int sp_heads_per_rank, int variant, void* stream) {
+    return gemm_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, act, epilogue, resid, ldr, gate, ld_gate, rows_per_sample,
+                     rope_cos, rope_sin, qk_cols, eps, sp_ranks, sp_heads_per_rank, variant, stream, nullptr);
+}
+
+int flite_gemm_qkv_p2p(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, const void* bias,
+                       int tokens_per_sample, const void* rope_cos, const void* rope_sin, float eps, int sp_ranks,
+                       int sp_heads_per_rank, int sp_rank, int seq_len, void* const* peer_recv, int variant,
+                       void* stream) {
+    if (!peer_recv) return fail(FLITE_ERR_INVALID, "gemm_qkv_p2p: null peer table");
+    if (sp_rank < 0 || sp_rank >= sp_ranks || seq_len != tokens_per_sample * sp_ranks)
+        return fail(FLITE_ERR_INVALID, "gemm_qkv_p2p: inconsistent sequence-parallel geometry");
+    const int d = sp_ranks * sp_heads_per_rank * 256;
+    SpPeers peers{peer_recv, sp_rank, seq_len};
+    const int64_t ldc = 3 * (int64_t)sp_heads_per_rank * 256;
+    return gemm_impl(A, lda, W, ldw, peer_recv[sp_rank], ldc, M, 3 * d, K, bias, 0, EPI_QKV_ROPE, nullptr, 0, nullptr, 0,
+                     tokens_per_sample, rope_cos, rope_sin, 2 * d, eps, sp_ranks, sp_heads_per_rank, variant, stream,
+                     &peers);
+}
+
+struct AttnPeers {
+    void* const* ptrs;
+    int n, lq, head0;
+};
+
+static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                          int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
+                          const int* cu_q, const int* cu_k, int B, int H, int max_q, float softmax_scale,
+                          int variant, void* stream, const AttnPeers* peers) {
     if (!q || !k || !v || !out || !cu_q || !cu_k) return fail(FLITE_ERR_INVALID, "attention: null pointer");
     if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || q_col0 % 8 || k_col0 % 8 || v_col0 % 8)
         return fail(FLITE_ERR_INVALID, "attention: strides / column offsets must be multiples of 8");
@@ -453,6 +496,18 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     p.debug = g_tuning[FLITE_TUNE_ATTN_DEBUG];
+    for (int i = 0; i < 8; ++i) p.out_peer[i] = nullptr;
+    p.sp_lq = 1; p.sp_head0 = 0;
+    if (peers) {
+        if (variant < FLITE_ATTN_2CTA_1WG || variant > FLITE_ATTN_2CTA_2WG_PTMEM)
+            return fail(FLITE_ERR_INVALID, "attention: the peer-memory output path needs a 2-CTA variant (3..6)");
+        if (peers->n <= 0 || peers->n > 8 || peers->lq <= 0) return fail(FLITE_ERR_INVALID, "attention: bad peer table");
+        for (int i = 0; i < peers->n; ++i) {
+            if (!peers->ptrs[i]) return fail(FLITE_ERR_INVALID, "attention: null peer buffer %d", i);
+            p.out_peer[i] = (__nv_bfloat16*)peers->ptrs[i];
+        }
+        p.sp_lq = peers->lq; p.sp_head0 = peers->head0;
+    }
     const int q_tiles = (max_q + 127) / 128;
     if (qtmem) {
         CUtensorMap tk2, tv2;
@@ -511,6 +566,72 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
         case FLITE_ATTN_2CTA_1WG_PTMEM: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<1, true>, tq, tk, tv, p)); break;
         default: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<2, true>, tq, tk, tv, p)); break;
     }
+    return 0;
+}
+
+int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                           int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
+                           const int* cu_q, const int* cu_k, int B, int H, int max_q, float softmax_scale,
+                           int variant, void* stream) {
+    return attention_impl(q, ldq, rows_q, q_col0, k, ldk, rows_k, k_col0, v, ldv, v_col0, out, ldo, cu_q, cu_k, B, H,
+                          max_q, softmax_scale, variant, stream, nullptr);
+}
+
+int flite_attention_varlen_p2p(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                               int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0,
+                               void* const* peer_out, int n_peers, int tokens_per_rank, int head0, int64_t ldo,
+                               const int* cu_q, const int* cu_k, int B, int H, int max_q, float softmax_scale,
+                               int variant, void* stream) {
+    if (!peer_out) return fail(FLITE_ERR_INVALID, "attention_p2p: null peer table");
+    AttnPeers peers{peer_out, n_peers, tokens_per_rank, head0};
+    return attention_impl(q, ldq, rows_q, q_col0, k, ldk, rows_k, k_col0, v, ldv, v_col0, peer_out[0], ldo, cu_q, cu_k,
+                          B, H, max_q, softmax_scale, variant, stream, &peers);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Peer (NVLink) memory plumbing for the fused exchange: symmetric allocations shared between the ranks of one node
+// through CUDA IPC handles, and stream-ordered completion flags.
+// ---------------------------------------------------------------------------------------------------------------
+int flite_p2p_alloc(int64_t bytes, void** out) {
+    if (!out || bytes <= 0) return fail(FLITE_ERR_INVALID, "p2p_alloc: bad arguments");
+    CUDA_TRY(cudaMalloc(out, (size_t)bytes));
+    CUDA_TRY(cudaMemset(*out, 0, (size_t)bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+int flite_p2p_free(void* p) {
+    if (p) CUDA_TRY(cudaFree(p));
+    return 0;
+}
+int flite_ipc_get_handle(const void* p, void* handle64) {
+    if (!p || !handle64) return fail(FLITE_ERR_INVALID, "ipc_get_handle: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), const_cast<void*>(p)));
+    return 0;
+}
+int flite_ipc_open(const void* handle64, void** out) {
+    if (!handle64 || !out) return fail(FLITE_ERR_INVALID, "ipc_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int flite_ipc_close(void* p) {
+    if (p) CUDA_TRY(cudaIpcCloseMemHandle(p));
+    return 0;
+}
+int flite_p2p_signal(void* const* peer_flags, int n, int my_slot, unsigned int value, void* stream) {
+    if (!peer_flags || n <= 0 || n > 8 || my_slot < 0 || my_slot >= 8) return fail(FLITE_ERR_INVALID, "p2p_signal: bad arguments");
+    PeerFlagPtrs pf;
+    for (int i = 0; i < 8; ++i) pf.p[i] = i < n ? (unsigned int*)peer_flags[i] : nullptr;
+    p2p_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, n, my_slot, value);
+    LAUNCH_CHECK();
+    return 0;
+}
+int flite_p2p_wait(const void* my_flags, int n, unsigned int value, void* stream) {
+    if (!my_flags || n <= 0 || n > 8) return fail(FLITE_ERR_INVALID, "p2p_wait: bad arguments");
+    p2p_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned int*)my_flags, n, value);
+    LAUNCH_CHECK();
     return 0;
 }
 

@@ -43,6 +43,12 @@ struct GemmParams {
     int sp_ranks;
     int sp_hp;                   // heads per rank
     int n_heads;
+    // Fused exchange: when sp_peer[0] != nullptr the head is stored straight into the DESTINATION rank's receive buffer
+    // over NVLink peer memory ([sample][full sequence][q|k|v of that rank's heads], row = smp*sp_seq + sp_rank*Lq + li)
+    // instead of a local all-to-all send buffer.
+    __nv_bfloat16* sp_peer[8];
+    int sp_rank;
+    int sp_seq;
     // Tail balancing: work units [0, full_units) are whole tiles; units beyond are HALF tiles (BLOCK_N/2 columns)
     // of the remaining tiles, so that a last partial wave is spread over twice as many clusters.
     int full_units;              // == number of tiles when no split is used
@@ -375,13 +381,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (row_ok) {
                     const float rstd = do_norm ? rsqrtf(ssq * (1.0f / 256.0f) + p.eps) : 1.0f;
                     long long out_off = (long long)row * p.ldc + n0;
+                    __nv_bfloat16* out_base = p.C;
                     if (p.sp_ranks > 0) {
                         const int t = n0 >> 8, which = t / p.n_heads, head = t % p.n_heads;
                         const int smp = row / p.rows_per_sample, li = row % p.rows_per_sample;
-                        const long long drow = ((long long)smp * p.sp_ranks + head / p.sp_hp) * p.rows_per_sample + li;
-                        out_off = drow * p.ldc + (long long)which * p.sp_hp * 256 + (head % p.sp_hp) * 256;
+                        const int dst = head / p.sp_hp;
+                        const long long col = (long long)which * p.sp_hp * 256 + (head % p.sp_hp) * 256;
+                        if (p.sp_peer[0] != nullptr) {
+                            const long long drow = (long long)smp * p.sp_seq + (long long)p.sp_rank * p.rows_per_sample + li;
+                            out_off = drow * p.ldc + col;
+                            out_base = p.sp_peer[dst];
+                        } else {
+                            const long long drow = ((long long)smp * p.sp_ranks + dst) * p.rows_per_sample + li;
+                            out_off = drow * p.ldc + col;
+                        }
                     }
-                    uint4* cp = reinterpret_cast<uint4*>(p.C + out_off);
+                    uint4* cp = reinterpret_cast<uint4*>(out_base + out_off);
 #pragma unroll
                     for (int u = 0; u < 32; ++u) {
                         uint32_t o[4];

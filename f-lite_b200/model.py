@@ -182,6 +182,8 @@ class DiT(nn.Module):
         self.hoist_context = True
         self.gemm_variant = GEMM_AUTO
         self.sp_group = None      # Ulysses sequence-parallel process group (see enable_sequence_parallel)
+        self.sp_fused = False     # exchanges fused into the kernels over NVLink peer memory instead of NCCL
+        self._sp_sym = None
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -192,16 +194,39 @@ class DiT(nn.Module):
     def device(self):
         return self.context_proj.weight.device
 
-    def enable_sequence_parallel(self, group):
+    def enable_sequence_parallel(self, group, fused: bool = False):
         """Ulysses sequence parallelism over ``group``: every rank holds
         L/P tokens of each sequence; self-attention is computed head-sharded over the full sequence with two
-        all-to-alls per block (NCCL over NVLink); everything else is token-local.  ``None`` disables it."""
+        exchanges per block; everything else is token-local.  ``None`` disables it.
+
+        ``fused=False``: the exchanges are NCCL ``all_to_all_single`` calls.  ``fused=True``: the QKV GEMM epilogue
+        and the attention epilogue store straight into the destination rank's buffer over NVLink peer memory
+        (``peer.SymmetricBuffer``; CUDA IPC, all ranks on one node) and only a flag handshake separates the kernels,
+        so the transfer overlaps the math tile by tile and the permute/copy kernels disappear."""
         if group is not None:
             import torch.distributed as dist
             P = dist.get_world_size(group)
             if self.config.num_heads % P:
                 raise FliteError(f"sequence parallel degree {P} must divide num_heads {self.config.num_heads}")
+        if self._sp_sym is not None:
+            self._sp_sym[1].close()
+            self._sp_sym = None
         self.sp_group = group
+        self.sp_fused = bool(fused) and group is not None
+
+    def _sym(self, B, L, Lq, dq, d, dev):
+        """Symmetric peer buffer: [receive q|k|v of my heads for the full sequences | returned attention rows]."""
+        key = (B, L, Lq, dq, d, str(dev))
+        if self._sp_sym is None or self._sp_sym[0] != key:
+            from .peer import SymmetricBuffer
+            if self._sp_sym is not None:
+                self._sp_sym[1].close()
+            recv_elems = B * L * 3 * dq
+            sym = SymmetricBuffer(self.sp_group, 2 * (recv_elems + B * Lq * d), dev)
+            recv = sym.local[:recv_elems].view(B * L, 3 * dq)
+            ao = sym.local[recv_elems:recv_elems + B * Lq * d].view(B * Lq, d)
+            self._sp_sym = (key, sym, recv, ao, sym.table(0), sym.table(2 * recv_elems))
+        return self._sp_sym[1:]
 
     def _check_ready(self):
         w = self.context_proj.weight
@@ -360,6 +385,10 @@ class DiT(nn.Module):
             qkv = self._buf("qkv", (T, 3 * d), dev)
         else:
             hq, dq = nh // P, d // P                                 # heads / width of this rank's head group
+        if sp is not None and self.sp_fused:
+            sym, p2p_recv, p2p_ao, recv_tab, ao_tab = self._sym(B, L, Lq, dq, d, dev)
+            stream = torch.cuda.current_stream().cuda_stream
+        elif sp is not None:
             a2a_send = self._buf("a2a_send", (B, P * Lq, 3 * dq), dev)   # [sample][dest rank][local token][q|k|v]
             a2a_recv = self._buf("a2a_recv", (B, L, 3 * dq), dev)        # [sample][full sequence][q|k|v of my heads]
             ao_full = self._buf("ao_full", (B, L, dq), dev)
@@ -373,6 +402,16 @@ class DiT(nn.Module):
                 ops.gemm(nbuf, sa.qkv.weight, sa.qkv.bias, epilogue=EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin,
                          qk_cols=2 * d, rows_per_sample=Lq, variant=v, out=qkv)
                 ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu_x, cu_x, nh, L, scale, out=abuf)
+            elif self.sp_fused:
+                # Ulysses over peer memory: the QKV epilogue stores each head into its owner's receive buffer, the
+                # attention epilogue stores each query row into the token owner's buffer; flags order the kernels.
+                ops.gemm_qkv_p2p(nbuf, sa.qkv.weight, sa.qkv.bias, cos, sin, Lq, P, hq, rk, L, recv_tab, variant=v)
+                sym.exchange_done(stream)
+                ops.attention_varlen_p2p(p2p_recv[:, :dq], p2p_recv[:, dq:2 * dq], p2p_recv[:, 2 * dq:], cu_full,
+                                         cu_full, hq, L, scale, ao_tab, P, Lq, rk * hq, d)
+                sym.exchange_done(stream)
+                ops.gemm(p2p_ao, sa.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_sa,
+                         rows_per_sample=Lq, variant=v, out=xs)
             else:
                 # Ulysses: the QKV epilogue scatters heads into the all-to-all send layout; after the exchange this
                 # rank holds q|k|v of its hq heads for the FULL sequence; the second exchange returns the outputs.
@@ -388,8 +427,9 @@ class DiT(nn.Module):
                     dist.all_to_all_single(ao_recv[b], ao_full[b], group=sp)
                 for b in range(B):   # [source rank][token][dq] -> [token][source rank * dq] = head-major columns
                     ops.permute_021(ao_recv[b].view(P, Lq, dq), out=abuf[b * Lq:(b + 1) * Lq].view(Lq, P, dq))
-            ops.gemm(abuf, sa.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_sa,
-                     rows_per_sample=Lq, variant=v, out=xs)
+            if not (sp is not None and self.sp_fused):
+                ops.gemm(abuf, sa.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_sa,
+                         rows_per_sample=Lq, variant=v, out=xs)
             # ---- cross-attention (model.py:291-297): token-local, context K/V replicated
             if blk.cross_attn is not None:
                 ca = blk.cross_attn

@@ -217,6 +217,48 @@ def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: to
     return out
 
 
+def gemm_qkv_p2p(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], rope_cos: torch.Tensor,
+                 rope_sin: torch.Tensor, tokens_per_sample: int, sp_ranks: int, sp_heads_per_rank: int, sp_rank: int,
+                 seq_len: int, peer_recv, eps: float = 1e-6, variant: int = GEMM_AUTO) -> None:
+    """Fused QKV projection + head all-to-all: ``a @ w.T`` (+bias, RoPE, QK-norm, model.py:162-183) with every head
+    stored straight into the receive buffer of the rank that owns it over NVLink peer memory.  ``peer_recv`` is a
+    ctypes array of the ranks' receive-buffer addresses (``peer.SymmetricBuffer.table``)."""
+    lib = _lib.load()
+    _chk(a, "a")
+    _chk(w, "w")
+    for t, n in ((bias, "bias"), (rope_cos, "rope_cos"), (rope_sin, "rope_sin")):
+        if t is not None:
+            _chk(t, n)
+    M, K = a.shape
+    if w.shape[0] != 3 * sp_ranks * sp_heads_per_rank * 256:
+        raise _lib.FliteError("gemm_qkv_p2p: weight rows must be 3 * heads * 256")
+    _lib.check(lib.flite_gemm_qkv_p2p(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, K, _ptr(bias),
+                                      tokens_per_sample, _ptr(rope_cos), _ptr(rope_sin), eps, sp_ranks,
+                                      sp_heads_per_rank, sp_rank, seq_len, peer_recv, variant, _stream()),
+               "gemm_qkv_p2p")
+    LAUNCHES[0] += 1
+
+
+def attention_varlen_p2p(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: torch.Tensor, cu_k: torch.Tensor,
+                         num_heads: int, max_q: int, softmax_scale: float, peer_out, n_peers: int,
+                         tokens_per_rank: int, head0: int, ldo: int, variant: int = 0) -> None:
+    """Fused attention + return all-to-all: query row l of this rank's ``num_heads`` heads is stored into the buffer of
+    the rank that owns token l (``peer_out[l // tokens_per_rank]``, row ``b*tokens_per_rank + l % tokens_per_rank``,
+    columns ``(head0 + h) * 256``, row stride ``ldo``)."""
+    lib = _lib.load()
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, n)
+    _chk(cu_q, "cu_q", torch.int32)
+    _chk(cu_k, "cu_k", torch.int32)
+    B = cu_q.numel() - 1
+    _lib.check(lib.flite_attention_varlen_p2p(q.data_ptr(), q.stride(0), q.shape[0], 0, k.data_ptr(), k.stride(0),
+                                              k.shape[0], 0, v.data_ptr(), v.stride(0), 0, peer_out, n_peers,
+                                              tokens_per_rank, head0, ldo, cu_q.data_ptr(), cu_k.data_ptr(), B,
+                                              num_heads, max_q, float(softmax_scale), variant, _stream()),
+               "attention_varlen_p2p")
+    LAUNCHES[0] += 1
+
+
 def permute_021(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[n0, n1, n2] -> [n1, n0, n2] (bf16 contiguous, n2 % 8 == 0)."""
     lib = _lib.load()

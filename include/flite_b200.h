@@ -142,6 +142,35 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
                            int64_t ldo, const int* cu_q, const int* cu_k, int B, int H, int max_q,
                            float softmax_scale, int variant, void* stream);
 
+/* ---- fused compute + exchange over NVLink peer memory (Ulysses sequence parallelism) ----
+ * flite_gemm_qkv_p2p: the QKV projection (+bias, RoPE, QK-norm) whose epilogue stores every head straight into the
+ *   receive buffer of the rank that owns it: peer_recv[g][(sample*seq_len + sp_rank*tokens_per_sample + t), q|k|v][..]
+ *   (row stride 3*sp_heads_per_rank*256).  Replaces GEMM -> all_to_all.
+ * flite_attention_varlen_p2p: attention over the full sequence for this rank's heads whose epilogue stores each query
+ *   row into the buffer of the rank that owns the token: peer_out[l / tokens_per_rank][(b*tokens_per_rank + l %
+ *   tokens_per_rank), (head0 + h)*256 ..] (row stride ldo).  Replaces attention -> all_to_all -> permute.
+ * peer_* are HOST arrays of device pointers valid in this process (own allocation + cudaIpcOpenMemHandle of peers). */
+int flite_gemm_qkv_p2p(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, const void* bias,
+                       int tokens_per_sample, const void* rope_cos, const void* rope_sin, float eps, int sp_ranks,
+                       int sp_heads_per_rank, int sp_rank, int seq_len, void* const* peer_recv, int variant,
+                       void* stream);
+int flite_attention_varlen_p2p(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                               int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0,
+                               void* const* peer_out, int n_peers, int tokens_per_rank, int head0, int64_t ldo,
+                               const int* cu_q, const int* cu_k, int B, int H, int max_q, float softmax_scale,
+                               int variant, void* stream);
+
+/* Symmetric peer allocations (cudaMalloc + CUDA IPC) and stream-ordered cross-GPU completion flags.
+ *   signal: after all prior work of `stream`, write `value` into slot my_slot of each peer's flag array (uint32[8]);
+ *   wait:   block `stream` until slots [0, n) of the local flag array are >= value (monotonic epochs; 5 s watchdog). */
+int flite_p2p_alloc(int64_t bytes, void** out);
+int flite_p2p_free(void* p);
+int flite_ipc_get_handle(const void* p, void* handle64);
+int flite_ipc_open(const void* handle64, void** out);
+int flite_ipc_close(void* p);
+int flite_p2p_signal(void* const* peer_flags, int n, int my_slot, unsigned int value, void* stream);
+int flite_p2p_wait(const void* my_flags, int n, unsigned int value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ ap.add_argument("--cfg-ranks", type=int, default=1)
 ap.add_argument("--sp-ranks", type=int, default=1)
 ap.add_argument("--big", action="store_true", help="time the 10B architecture at 2048^2 (config C4)")
 ap.add_argument("--res", type=int, default=2048)
+ap.add_argument("--fused", action="store_true", help="Ulysses exchanges fused into the kernels over NVLink peer memory")
 args = ap.parse_args()
 local = int(os.environ.get("LOCAL_RANK", 0)); rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
@@ -31,7 +32,7 @@ def build(cfg, seed=0):
         else: p.data.copy_(torch.randn(p.shape, device=dev, generator=g) * (0.02 if p.dim() < 2 or n.startswith(("adaLN", "final", "register")) else p.shape[-1] ** -0.5))
     return m.eval()
 
-out = {"world": world, "cfg_ranks": args.cfg_ranks, "sp_ranks": args.sp_ranks}
+out = {"world": world, "cfg_ranks": args.cfg_ranks, "sp_ranks": args.sp_ranks, "fused": args.fused}
 # ---------------- parity on a small model (4 heads so that P = 2 or 4 divides)
 cfg = dict(in_channels=16, patch_size=2, hidden_size=1024, depth=3, num_heads=4, mlp_ratio=4.0, cross_attn_input_size=512)
 m = build(cfg)
@@ -46,6 +47,12 @@ if sp_group is not None:
     m.enable_sequence_parallel(sp_group)
     got = m(torch.cat([lat, lat]), torch.cat([neg, pos]), mask, t)
     out["sp_forward_rel"] = rel(got, ref)
+    if args.fused:
+        m.enable_sequence_parallel(sp_group, fused=True)
+        for it in range(3):   # repeated calls exercise the monotonic flag epochs / buffer reuse
+            got = m(torch.cat([lat, lat]), torch.cat([neg, pos]), mask, t)
+        out["sp_fused_forward_rel"] = rel(got, ref)
+        _lib.watchdog_ok()
 ref_lat = flite_b200.denoise(build(cfg), lat, neg, pos, mask, 3, 6.0)
 got_lat = flite_b200.denoise(m, lat, neg, pos, mask, 3, 6.0, cfg_group=cfg_group)
 out["denoise_rel"] = rel(got_lat, ref_lat)
@@ -58,7 +65,7 @@ if args.big:
     cfg = dict(in_channels=16, patch_size=2, hidden_size=3072, depth=40, num_heads=12, mlp_ratio=4.0, cross_attn_input_size=4096)
     m = build(cfg)
     m.hoist_context = False
-    if sp_group is not None: m.enable_sequence_parallel(sp_group)
+    if sp_group is not None: m.enable_sequence_parallel(sp_group, fused=args.fused)
     R = args.res // 8
     lat = torch.randn(1, 16, R, R, device=dev, generator=g).bfloat16(); acc = lat.clone()
     pos = torch.randn(1, 256, 4096, device=dev, generator=g).bfloat16(); neg = torch.zeros_like(pos)
@@ -82,5 +89,5 @@ if args.big:
 if rank == 0:
     print("MGPU", json.dumps(out), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open(f"gpurun_out/mgpu_w{world}_c{args.cfg_ranks}_s{args.sp_ranks}.json", "w"))
+    json.dump(out, open(f"gpurun_out/mgpu_w{world}_c{args.cfg_ranks}_s{args.sp_ranks}{'_fused' if args.fused else ''}.json", "w"))
 dist.destroy_process_group()
