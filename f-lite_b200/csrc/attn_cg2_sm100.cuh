@@ -291,6 +291,36 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             mbar_wait<true>(pv_done, (n_tiles - 1) & 1, 29);
             tc_fence_after();
             const float inv_l = 1.0f / l;
+            if (p.stage_out) {
+                // Whole-row stores (NVLink peer destinations): all MMAs have completed (pv_done), so the Q tile in
+                // shared memory is dead; each warp transposes its 32 rows through it -- lane = row on the way in,
+                // lane = 16-byte chunk on the way out (32 / CH rows of OC*2 contiguous bytes per store instruction).
+                constexpr int CH = OC / 8;                       // 16-byte chunks per row segment
+                uint8_t* stg = smem + ATT2_SQ + (warp_idx - 2) * (32 * OC * 2);
+                const unsigned long long my_ptr = row_ok ? (unsigned long long)orow : 0ull;
+#pragma unroll 1
+                for (int c = 0; c < OC / 32; ++c) {
+                    uint32_t o[32];
+                    tmem_ld_x32(tmem_o + lane_off + half * OC + c * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(stg + lane * (OC * 2) + (((c * 4 + i) ^ (lane & (CH - 1))) << 4)) = make_uint4(
+                            pack_bf16x2(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
+                }
+                __syncwarp();
+                const int cc = lane & (CH - 1);
+#pragma unroll 4
+                for (int i2 = 0; i2 < CH; ++i2) {
+                    const int rr = i2 * (32 / CH) + lane / CH;
+                    const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * (OC * 2) + ((cc ^ (rr & (CH - 1))) << 4));
+                    const unsigned long long rp = __shfl_sync(0xffffffffu, my_ptr, rr);
+                    if (rp != 0ull) reinterpret_cast<uint4*>(rp)[cc] = v;
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < OC / 32; ++c) {
                 uint32_t o[32];
@@ -306,6 +336,7 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                             pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
                             pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
                 }
+            }
             }
         } else if (row_ok) {
             // empty key sequence: flash-attn returns zeros

@@ -34,6 +34,7 @@ struct AttnParams {
     __nv_bfloat16* out_peer[8];
     int sp_lq;
     int sp_head0;
+    int stage_out;          // attn_fwd_cg2_kernel: 1 = store whole output rows via a shared-memory transpose
 };
 
 constexpr int ATT_SQ = 0, ATT_SK = 65536, ATT_SV = 131072, ATT_SP = 196608, ATT_BAR = 229376;

@@ -130,7 +130,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     auto kern = gemm_bf16_kernel<kCtaGroup, BLOCK_N, kStages, kEpi>;
     static bool configured = false;
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kEpi == EPI_QKV_ROPE ? S::TOTAL_STAGED : S::TOTAL));
         configured = true;
     }
     const int tile_m = 128 * kCtaGroup;
@@ -171,7 +172,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * kCtaGroup);
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.dynamicSmemBytes = (kEpi == EPI_QKV_ROPE && p.stage_stores) ? S::TOTAL_STAGED : S::TOTAL;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -419,6 +420,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
         p.sp_rank = peers->rank;
         p.sp_seq = peers->seq_len;
     }
+    p.stage_stores = (epilogue == EPI_QKV_ROPE && (peers != nullptr || g_tuning[FLITE_TUNE_QKV_STAGED_STORES])) ? 1 : 0;
 
     CUtensorMap ta, tb, tbh;
     int rc = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128);
@@ -508,6 +510,7 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
         }
         p.sp_lq = peers->lq; p.sp_head0 = peers->head0;
     }
+    p.stage_out = (peers != nullptr || g_tuning[FLITE_TUNE_ATTN_STAGED_STORES]) ? 1 : 0;
     const int q_tiles = (max_q + 127) / 128;
     if (qtmem) {
         CUtensorMap tk2, tv2;

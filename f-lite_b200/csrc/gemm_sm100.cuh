@@ -49,6 +49,9 @@ struct GemmParams {
     __nv_bfloat16* sp_peer[8];
     int sp_rank;
     int sp_seq;
+    // EPI_QKV_ROPE: 1 = transpose each warp's 32 rows through shared memory so that every store instruction writes
+    // whole 256-byte row segments (needed for NVLink efficiency when the destination is a peer GPU)
+    int stage_stores;
     // Tail balancing: work units [0, full_units) are whole tiles; units beyond are HALF tiles (BLOCK_N/2 columns)
     // of the remaining tiles, so that a last partial wave is spread over twice as many clusters.
     int full_units;              // == number of tiles when no split is used
@@ -68,7 +71,10 @@ struct GemmSmem {
     static constexpr int B_BYTES = BN_CTA * GEMM_BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = kStages * STAGE_BYTES;
+    static constexpr int STAGING_OFFSET = BAR_OFFSET + 256;           // 4 epilogue warps x 32 rows x 256 B
+    static constexpr int STAGING_BYTES = 4 * 32 * 256;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+    static constexpr int TOTAL_STAGED = TOTAL + STAGING_BYTES;
 };
 
 template <int kCtaGroup, int BLOCK_N, int kStages, int kEpi>
@@ -378,24 +384,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
                 }
                 __syncwarp();
-                if (row_ok) {
-                    const float rstd = do_norm ? rsqrtf(ssq * (1.0f / 256.0f) + p.eps) : 1.0f;
-                    long long out_off = (long long)row * p.ldc + n0;
-                    __nv_bfloat16* out_base = p.C;
-                    if (p.sp_ranks > 0) {
-                        const int t = n0 >> 8, which = t / p.n_heads, head = t % p.n_heads;
-                        const int smp = row / p.rows_per_sample, li = row % p.rows_per_sample;
-                        const int dst = head / p.sp_hp;
-                        const long long col = (long long)which * p.sp_hp * 256 + (head % p.sp_hp) * 256;
-                        if (p.sp_peer[0] != nullptr) {
-                            const long long drow = (long long)smp * p.sp_seq + (long long)p.sp_rank * p.rows_per_sample + li;
-                            out_off = drow * p.ldc + col;
-                            out_base = p.sp_peer[dst];
-                        } else {
-                            const long long drow = ((long long)smp * p.sp_ranks + dst) * p.rows_per_sample + li;
-                            out_off = drow * p.ldc + col;
-                        }
+                const float rstd = do_norm ? rsqrtf(ssq * (1.0f / 256.0f) + p.eps) : 1.0f;
+                long long out_off = (long long)row * p.ldc + n0;
+                __nv_bfloat16* out_base = p.C;
+                if (p.sp_ranks > 0) {
+                    const int t = n0 >> 8, which = t / p.n_heads, head = t % p.n_heads;
+                    const int rr = row_ok ? row : 0;
+                    const int smp = rr / p.rows_per_sample, li = rr % p.rows_per_sample;
+                    const int dst = head / p.sp_hp;
+                    const long long col = (long long)which * p.sp_hp * 256 + (head % p.sp_hp) * 256;
+                    if (p.sp_peer[0] != nullptr) {
+                        const long long drow = (long long)smp * p.sp_seq + (long long)p.sp_rank * p.rows_per_sample + li;
+                        out_off = drow * p.ldc + col;
+                        out_base = p.sp_peer[dst];
+                    } else {
+                        const long long drow = ((long long)smp * p.sp_ranks + dst) * p.rows_per_sample + li;
+                        out_off = drow * p.ldc + col;
                     }
+                }
+                if (p.stage_stores) {
+                    // warp-local transpose through shared memory: lane = row on the way in, lane = 16-byte chunk of a
+                    // row on the way out (two rows of 256 B per store instruction); chunks XOR-swizzled by the row
+                    uint8_t* stg = smem + S::STAGING_OFFSET + (warp_idx - 2) * (32 * 256);
+                    const unsigned long long my_ptr = row_ok ? (unsigned long long)(out_base + out_off) : 0ull;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t v = keep[hf * 64 + 4 * u + j];
+                                o[j] = do_norm ? pack_bf16x2(bf16_lo(v) * rstd, bf16_hi(v) * rstd) : v;
+                            }
+                            *reinterpret_cast<uint4*>(stg + lane * 256 + ((u ^ (lane & 15)) << 4)) =
+                                make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                        __syncwarp();
+                        const int c = lane & 15;
+#pragma unroll 4
+                        for (int i2 = 0; i2 < 16; ++i2) {
+                            const int r = 2 * i2 + (lane >> 4);
+                            const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 256 + ((c ^ (r & 15)) << 4));
+                            const unsigned long long rp = __shfl_sync(0xffffffffu, my_ptr, r);
+                            if (rp != 0ull) reinterpret_cast<uint4*>(rp)[hf * 16 + c] = v;
+                        }
+                        __syncwarp();
+                    }
+                } else if (row_ok) {
                     uint4* cp = reinterpret_cast<uint4*>(out_base + out_off);
 #pragma unroll
                     for (int u = 0; u < 32; ++u) {

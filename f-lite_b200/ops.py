@@ -21,6 +21,41 @@ LAUNCHES = [0]
 PROFILE_HOOK = None
 
 
+# Per-op device timing (tools/mgpu_check.py --trace, tools/profile_step.py): when TRACE is a list every public op
+# below appends (label, start_event, end_event) recorded on the launching stream; trace_report() aggregates them.
+TRACE = None
+
+
+def _traced(label_fn):
+    def deco(fn):
+        def wrapper(*args, **kwargs):
+            tr = TRACE
+            if tr is None:
+                return fn(*args, **kwargs)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*args, **kwargs)
+            e1.record()
+            tr.append((label_fn(*args, **kwargs), e0, e1))
+            return r
+        wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+        return wrapper
+    return deco
+
+
+def trace_report():
+    """{label: (launches, total_ms)} of the ops recorded since TRACE was set; synchronises."""
+    torch.cuda.synchronize()
+    agg = {}
+    for label, e0, e1 in TRACE or []:
+        n, ms = agg.get(label, (0, 0.0))
+        agg[label] = (n + 1, ms + e0.elapsed_time(e1))
+    return agg
+
+
+_EPI_NAMES = {EPI_STORE: "store", EPI_GATED_RES: "gated_res", EPI_SWIGLU: "swiglu", EPI_QKV_ROPE: "qkv_rope"}
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -57,6 +92,7 @@ def cfg_euler(acc: torch.Tensor, v_uncond: Optional[torch.Tensor], v_cond: torch
     LAUNCHES[0] += 1
 
 
+@_traced(lambda x, *a, **k: f"rmsnorm_modulate {tuple(x.shape)}")
 def rmsnorm_modulate(x: torch.Tensor, weight: Optional[torch.Tensor], weight_mode: int,
                      scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
                      rows_per_sample: int = 0, eps: float = 1e-6, out: Optional[torch.Tensor] = None):
@@ -156,6 +192,8 @@ def pack_context(src: torch.Tensor, mask_f32: torch.Tensor):
     return dst, cu
 
 
+@_traced(lambda a, w, *r, **k: f"gemm {_EPI_NAMES[k.get('epilogue', EPI_STORE)]} {a.shape[0]}x{w.shape[0]}x{a.shape[1]}"
+         + (" sp-scatter" if k.get("sp_ranks", 0) else ""))
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = 0,
          epilogue: int = EPI_STORE, resid: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
          rows_per_sample: int = 0, rope_cos: Optional[torch.Tensor] = None, rope_sin: Optional[torch.Tensor] = None,
@@ -196,6 +234,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+@_traced(lambda q, k, v, cu_q, cu_k, num_heads, max_q, *r, **kw: f"attention Tq={q.shape[0]} Tk={k.shape[0]} H={num_heads}")
 def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: torch.Tensor, cu_k: torch.Tensor,
                      num_heads: int, max_q: int, softmax_scale: float, out: Optional[torch.Tensor] = None,
                      variant: int = 0):
@@ -217,6 +256,7 @@ def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: to
     return out
 
 
+@_traced(lambda a, w, *r, **k: f"gemm qkv_rope+p2p {a.shape[0]}x{w.shape[0]}x{a.shape[1]}")
 def gemm_qkv_p2p(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], rope_cos: torch.Tensor,
                  rope_sin: torch.Tensor, tokens_per_sample: int, sp_ranks: int, sp_heads_per_rank: int, sp_rank: int,
                  seq_len: int, peer_recv, eps: float = 1e-6, variant: int = GEMM_AUTO) -> None:
@@ -239,6 +279,7 @@ def gemm_qkv_p2p(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
     LAUNCHES[0] += 1
 
 
+@_traced(lambda q, k, v, cu_q, cu_k, num_heads, *r, **kw: f"attention+p2p Tq={q.shape[0]} Tk={k.shape[0]} H={num_heads}")
 def attention_varlen_p2p(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: torch.Tensor, cu_k: torch.Tensor,
                          num_heads: int, max_q: int, softmax_scale: float, peer_out, n_peers: int,
                          tokens_per_rank: int, head0: int, ldo: int, variant: int = 0) -> None:
@@ -259,6 +300,7 @@ def attention_varlen_p2p(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q
     LAUNCHES[0] += 1
 
 
+@_traced(lambda src, *r, **k: f"permute_021 {tuple(src.shape)}")
 def permute_021(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[n0, n1, n2] -> [n1, n0, n2] (bf16 contiguous, n2 % 8 == 0)."""
     lib = _lib.load()

@@ -77,10 +77,19 @@ class SymmetricBuffer:
     def exchange_done(self, stream: int) -> None:
         """Stream-ordered all-to-all completion: publish "my stores up to here are done" to every peer, then block
         the stream until every peer has published the same epoch."""
+        from . import ops
         lib = _lib.load()
         self.epoch = (self.epoch + 1) & 0xFFFFFFFF
+        tr = ops.TRACE
+        if tr is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(lib.flite_p2p_signal(self.flag_ptrs, self.world, self.rank, self.epoch, stream), "p2p_signal")
         _lib.check(lib.flite_p2p_wait(self._base, self.world, self.epoch, stream), "p2p_wait")
+        ops.LAUNCHES[0] += 2
+        if tr is not None:
+            e1.record()
+            tr.append(("p2p signal+wait", e0, e1))
 
     def close(self) -> None:
         if self._base is None:

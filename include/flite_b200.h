@@ -61,6 +61,8 @@ extern "C" {
 #define FLITE_TUNE_GEMM_VARIANT 2    /* default GEMM variant when the call passes FLITE_GEMM_AUTO (0 = heuristic) */
 #define FLITE_TUNE_ATTN_DEBUG 3      /* profiling experiments only: bit0 skip softmax math, bit1 skip K/V reloads */
 #define FLITE_TUNE_GEMM_TAIL_SPLIT 4 /* 0 = run a last partial wave as half-width tiles (default), 1 = off */
+#define FLITE_TUNE_QKV_STAGED_STORES 6 /* 1 = QKV epilogue stores whole row segments via a shared-memory transpose (always on for peer stores) */
+#define FLITE_TUNE_ATTN_STAGED_STORES 7 /* 1 = 2-CTA attention stores whole output rows via a shared-memory transpose (always on for peer stores) */
 #define FLITE_TUNE_GEMM_BAND 5       /* 0 = L2-aware band rasterisation for large M (default), 1 = single band */
 int flite_set_tuning(int key, int value);
 

@@ -1,6 +1,8 @@
 """GPU parity tests, kernel by kernel, through the C ABI, against torch restatements of the reference ops."""
 import math
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -300,3 +302,110 @@ def test_patch_embed_token_slice_and_permute():
             assert torch.equal(part, full[:, r * Lq:(r + 1) * Lq])
     t = rnd(3, 5, 64, seed=5)
     assert torch.equal(ops.permute_021(t), t.permute(1, 0, 2).contiguous())
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("M", [2 * 272, 300, 2 * 4112])
+def test_qkv_epilogue_staged_stores_bit_equal(variant, M):
+    """FLITE_TUNE_QKV_STAGED_STORES: the shared-memory transposed store path (used for NVLink peer stores) writes
+    exactly what the one-row-per-thread path writes, ragged last M tile included."""
+    from flite_b200 import _lib, ops
+    d, L = 512, M // 2 if M % 2 == 0 else M
+    B = M // L
+    a, w, b = rnd(M, d, scale=0.5, seed=1), rnd(3 * d, d, scale=0.05, seed=2), rnd(3 * d, seed=3)
+    ang = torch.rand(L, 128, device=DEV) * 6.28
+    cos, sin = ang.cos().bfloat16(), ang.sin().bfloat16()
+    kw = dict(epilogue=ops.EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin, qk_cols=2 * d, rows_per_sample=L, variant=variant)
+    plain = ops.gemm(a, w, b, **kw)
+    lib = _lib.load()
+    lib.flite_set_tuning(6, 1)
+    try:
+        staged = torch.full((M + 8, 3 * d), 7.0, device=DEV, dtype=torch.bfloat16)   # guard rows catch overruns
+        ops.gemm(a, w, b, out=staged[:M], **kw)
+    finally:
+        lib.flite_set_tuning(6, 0)
+    assert torch.equal(staged[:M], plain)
+    assert bool((staged[M:] == 7.0).all())
+
+
+def _peer_table(bufs):
+    import ctypes
+    return (ctypes.c_void_p * 8)(*([t.data_ptr() for t in bufs] + [None] * (8 - len(bufs))))
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_fused_ulysses_kernels_single_gpu_loopback(P):
+    """The peer-memory kernels with every "peer" buffer on this GPU: P emulated ranks run flite_gemm_qkv_p2p /
+    flite_attention_varlen_p2p in turn; the receive buffers must equal what the all-to-all path produces and the
+    returned attention rows must equal single-GPU attention (SURVEY.md 8e, C4 layout)."""
+    from flite_b200 import ops
+    B, L, H = 2, 272, 4
+    d, Hp, Lq = H * 256, H // P, L // P
+    dq = d // P
+    x = rnd(B * L, d, scale=0.5, seed=1)
+    w, b = rnd(3 * d, d, scale=0.05, seed=2), rnd(3 * d, seed=3)
+    ang = torch.rand(L, 128, device=DEV) * 6.28
+    cos, sin = ang.cos().bfloat16(), ang.sin().bfloat16()
+    scale = 256 ** -0.5
+    cu = (torch.arange(0, B + 1, dtype=torch.int32) * L).to(DEV)
+    # single-GPU truth
+    qkv = ops.gemm(x, w, b, epilogue=ops.EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin, qk_cols=2 * d, rows_per_sample=L)
+    att = ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, H, L, scale)
+    # emulated ranks
+    recv = [torch.zeros(B * L, 3 * dq, device=DEV, dtype=torch.bfloat16) for _ in range(P)]
+    ao = [torch.zeros(B * Lq, d, device=DEV, dtype=torch.bfloat16) for _ in range(P)]
+    recv_tab, ao_tab = _peer_table(recv), _peer_table(ao)
+    xv = x.view(B, L, d)
+    for r in range(P):
+        xr = xv[:, r * Lq:(r + 1) * Lq].reshape(B * Lq, d).contiguous()
+        ops.gemm_qkv_p2p(xr, w, b, cos[r * Lq:(r + 1) * Lq].contiguous(), sin[r * Lq:(r + 1) * Lq].contiguous(),
+                         Lq, P, Hp, r, L, recv_tab)
+    q4 = qkv.view(B * L, 3, P, dq)
+    for r in range(P):
+        assert torch.equal(recv[r].view(B * L, 3, dq), q4[:, :, r])
+    for r in range(P):
+        rr = recv[r]
+        ops.attention_varlen_p2p(rr[:, :dq], rr[:, dq:2 * dq], rr[:, 2 * dq:], cu, cu, Hp, L, scale, ao_tab, P, Lq,
+                                 r * Hp, d)
+    got = torch.stack([a_.view(B, Lq, d) for a_ in ao], 1)          # [B, P, Lq, d]
+    got = got.permute(0, 1, 2, 3).reshape(B, P * Lq, d).reshape(B * L, d)
+    assert torch.equal(got, att)
+
+
+def test_p2p_flags_signal_then_wait_loopback():
+    """flite_p2p_signal / flite_p2p_wait on one GPU: two emulated ranks publish into the same flag array, the wait
+    returns once both slots carry the epoch (monotonic compare) and the watchdog stays clean."""
+    import ctypes
+    from flite_b200 import _lib
+    lib = _lib.load()
+    flags = torch.zeros(64, device=DEV, dtype=torch.int32)
+    tab = (ctypes.c_void_p * 8)(flags.data_ptr(), *([None] * 7))
+    s = torch.cuda.current_stream().cuda_stream
+    for epoch in (1, 2, 3):
+        for slot in (0, 1):
+            _lib.check(lib.flite_p2p_signal(tab, 1, slot, epoch, s), "signal")
+        _lib.check(lib.flite_p2p_wait(flags.data_ptr(), 2, epoch, s), "wait")
+    _lib.watchdog_ok()
+    assert flags[:2].tolist() == [3, 3]
+
+
+@pytest.mark.parametrize("variant", [3, 4, 5, 6])
+def test_attention_staged_output_stores_bit_equal(variant):
+    """FLITE_TUNE_ATTN_STAGED_STORES: whole-row output stores through the dead Q tile give the same bits as the
+    one-row-per-thread stores; ragged query tails and an empty key sequence included."""
+    from flite_b200 import _lib, ops
+    H = 2
+    q_lens, k_lens = [300, 1, 272], [129, 0, 272]
+    cu_q = torch.tensor([0] + list(np.cumsum(q_lens)), dtype=torch.int32, device=DEV)
+    cu_k = torch.tensor([0] + list(np.cumsum(k_lens)), dtype=torch.int32, device=DEV)
+    q, k, v = rnd(sum(q_lens), H * 256, seed=1), rnd(sum(k_lens), H * 256, seed=2), rnd(sum(k_lens), H * 256, seed=3)
+    plain = ops.attention_varlen(q, k, v, cu_q, cu_k, H, max(q_lens), 1 / 16, variant=variant)
+    lib = _lib.load()
+    lib.flite_set_tuning(7, 1)
+    try:
+        staged = torch.full((sum(q_lens) + 4, H * 256), 7.0, device=DEV, dtype=torch.bfloat16)
+        ops.attention_varlen(q, k, v, cu_q, cu_k, H, max(q_lens), 1 / 16, variant=variant, out=staged[:sum(q_lens)])
+    finally:
+        lib.flite_set_tuning(7, 0)
+    assert torch.equal(staged[:sum(q_lens)], plain)
+    assert bool((staged[sum(q_lens):] == 7.0).all())

@@ -14,6 +14,7 @@ ap.add_argument("--cfg-ranks", type=int, default=1)
 ap.add_argument("--sp-ranks", type=int, default=1)
 ap.add_argument("--big", action="store_true", help="time the 10B architecture at 2048^2 (config C4)")
 ap.add_argument("--res", type=int, default=2048)
+ap.add_argument("--trace", action="store_true", help="per-op CUDA-event breakdown of one step (rank 0 prints it)")
 ap.add_argument("--fused", action="store_true", help="Ulysses exchanges fused into the kernels over NVLink peer memory")
 args = ap.parse_args()
 local = int(os.environ.get("LOCAL_RANK", 0)); rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
@@ -85,6 +86,13 @@ if args.big:
     ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     out[f"c4_{args.res}_ms_per_step"] = ms.item()
+    if args.trace:
+        from flite_b200 import ops
+        ops.TRACE = []
+        e0.record(); step(); e1.record()
+        rep = ops.trace_report(); ops.TRACE = None
+        out["trace_step_ms"] = e0.elapsed_time(e1)
+        out["trace"] = {k: [n, round(ms, 3)] for k, (n, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1])}
     _lib.watchdog_ok()
 if rank == 0:
     print("MGPU", json.dumps(out), flush=True)
