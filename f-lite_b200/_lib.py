@@ -26,6 +26,10 @@ SIGNATURES = {
     "flite_set_tuning": [_I, _I],
     "flite_watchdog_status": [_P],
     "flite_cfg_euler": [_P, _I, _P, _P, _F, _F, _I, _P, _L, _P],
+    "flite_apg_workspace_bytes": [],
+    "flite_apg_euler": [_P, _I, _P, _P, _F, _F, _F, _P, _L, _P, _P],
+    "flite_latent_unscale": [_P, _P, _F, _F, _L, _P],
+    "flite_image_to_uint8": [_P, _I, _P, _I, _I, _I, _I, _P],
     "flite_rmsnorm_modulate": [_P, _L, _P, _L, _P, _I, _P, _P, _L, _I, _I, _I, _F, _P],
     "flite_rope_qknorm": [_P, _L, _I, _I, _P, _P, _I, _F, _P],
     "flite_patch_embed": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -409,4 +409,174 @@ cfg_euler_kernel(void* __restrict__ acc, int acc_is_fp32, const __nv_bfloat16* _
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Sampler, Augmented Parallel Guidance (f_lite/pipeline.py:276-287) fused with the Euler update.  The reference
+// evaluates three GLOBAL reductions over the whole batch tensor with torch ops in the model dtype:
+//   dy = c; dd = bf16(c - u); coef = bf16(bf16(sum(bf16(dy*dd))) / bf16(sum(bf16(dy*dy)))); par = bf16(coef*dy);
+//   orth = bf16(dd - par); std = bf16(unbiased std(orth)); scale = min(1, bf16(thr/std)); orth = bf16(orth*scale);
+//   v = bf16(dy + bf16((g-1)*orth));  acc += dt*v;  lat = bf16(acc)
+// Three stream-ordered launches share per-block fp64 partial sums in a caller-provided workspace (no host sync,
+// no atomics: every block re-reduces the partials in the same order, so the scalars are deterministic).
+// ------------------------------------------------------------------------------------------
+constexpr int APG_BLOCKS = 128;
+constexpr int APG_THREADS = 256;
+
+FLITE_DEVICE double apg_block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = (threadIdx.x < APG_THREADS / 32) ? sh[threadIdx.x] : 0.0;
+    if (w == 0) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (l == 0) sh[0] = t;
+    }
+    __syncthreads();
+    return sh[0];
+}
+// sum of the APG_BLOCKS partials at ws[0..APG_BLOCKS), same order in every block
+FLITE_DEVICE double apg_total(const double* ws, double* sh) {
+    return apg_block_sum(threadIdx.x < APG_BLOCKS ? ws[threadIdx.x] : 0.0, sh);
+}
+
+__global__ void __launch_bounds__(APG_THREADS)
+apg_dot_kernel(const __nv_bfloat16* __restrict__ v_uncond, const __nv_bfloat16* __restrict__ v_cond, long long n8,
+               double* __restrict__ ws) {
+    __shared__ double sh[APG_THREADS / 32];
+    double s1 = 0.0, s2 = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float c[8], u[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(v_cond) + i), c);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(v_uncond) + i), u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float dd = bf16_round(c[j] - u[j]);
+            s1 += (double)bf16_round(c[j] * dd);
+            s2 += (double)bf16_round(c[j] * c[j]);
+        }
+    }
+    const double t1 = apg_block_sum(s1, sh);
+    const double t2 = apg_block_sum(s2, sh);
+    if (threadIdx.x == 0) { ws[blockIdx.x] = t1; ws[APG_BLOCKS + blockIdx.x] = t2; }
+}
+
+FLITE_DEVICE float apg_coef(const double* ws, double* sh) {
+    const float s1 = bf16_round((float)apg_total(ws, sh));
+    const float s2 = bf16_round((float)apg_total(ws + APG_BLOCKS, sh));
+    return bf16_round(s1 / s2);
+}
+
+__global__ void __launch_bounds__(APG_THREADS)
+apg_orth_stats_kernel(const __nv_bfloat16* __restrict__ v_uncond, const __nv_bfloat16* __restrict__ v_cond,
+                      long long n8, double* __restrict__ ws) {
+    __shared__ double sh[APG_THREADS / 32];
+    const float coef = apg_coef(ws, sh);
+    double s1 = 0.0, s2 = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float c[8], u[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(v_cond) + i), c);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(v_uncond) + i), u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float orth = bf16_round(bf16_round(c[j] - u[j]) - bf16_round(coef * c[j]));
+            s1 += (double)orth;
+            s2 += (double)orth * (double)orth;
+        }
+    }
+    const double t1 = apg_block_sum(s1, sh);
+    const double t2 = apg_block_sum(s2, sh);
+    if (threadIdx.x == 0) { ws[2 * APG_BLOCKS + blockIdx.x] = t1; ws[3 * APG_BLOCKS + blockIdx.x] = t2; }
+}
+
+__global__ void __launch_bounds__(APG_THREADS)
+apg_euler_kernel(void* __restrict__ acc, int acc_is_fp32, const __nv_bfloat16* __restrict__ v_uncond,
+                 const __nv_bfloat16* __restrict__ v_cond, float gm1, float dt, float threshold,
+                 __nv_bfloat16* __restrict__ lat_out, long long n8, const double* __restrict__ ws) {
+    __shared__ double sh[APG_THREADS / 32];
+    const float coef = apg_coef(ws, sh);
+    const double n = (double)n8 * 8.0;
+    const double sum = apg_total(ws + 2 * APG_BLOCKS, sh), sq = apg_total(ws + 3 * APG_BLOCKS, sh);
+    const double mean = sum / n;
+    double var = (sq - n * mean * mean) / (n - 1.0);          // torch.std default: unbiased
+    if (var < 0.0) var = 0.0;
+    const float stdv = bf16_round((float)sqrt(var));
+    const float ratio = bf16_round(threshold / stdv);          // python float / 0-dim bf16 tensor -> bf16
+    const float scale = ratio < 1.0f ? ratio : 1.0f;           // min(1, ratio); NaN (std == 0) -> 1 like python's min
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float c[8], u[8], a[8], v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(v_cond) + i), c);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(v_uncond) + i), u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float orth = bf16_round(bf16_round(c[j] - u[j]) - bf16_round(coef * c[j]));
+            orth = bf16_round(orth * scale);
+            v[j] = bf16_round(c[j] + bf16_round(gm1 * orth));
+        }
+        if (acc_is_fp32) {
+            float4* ap = reinterpret_cast<float4*>(acc) + 2 * i;
+            float4 a0 = ap[0], a1 = ap[1];
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = a[j] + dt * v[j];
+            ap[0] = make_float4(a[0], a[1], a[2], a[3]);
+            ap[1] = make_float4(a[4], a[5], a[6], a[7]);
+        } else {
+            uint4* ap = reinterpret_cast<uint4*>(acc) + i;
+            unpack8(*ap, a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = bf16_round(a[j] + bf16_round(dt * v[j]));
+            *ap = pack8(a);
+        }
+        reinterpret_cast<uint4*>(lat_out)[i] = pack8(a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pipeline tail (f_lite/pipeline.py:299-327).
+//   latent_unscale : lat / scaling_factor + shift_factor   (pipeline.py:304), bf16 rounding points; like torch's CUDA
+//                    kernel for division by a host scalar the quotient is lat * (1 / scaling_factor) in fp32
+//   image_to_uint8 : (x / 2 + 0.5).clamp(0,1) * 255 -> round (half to even) -> uint8, NCHW -> NHWC
+//                    (pipeline.py:324-327: the reference keeps NCHW and permutes per image on the host)
+// in_is_fp32 selects the decoder dtype: bf16 reproduces the rounding after every torch op, fp32 computes in fp32.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+latent_unscale_kernel(const __nv_bfloat16* __restrict__ lat, __nv_bfloat16* __restrict__ out, float inv_scaling,
+                      float shift, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float a[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(lat) + i), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = bf16_round(bf16_round(a[j] * inv_scaling) + shift);
+        reinterpret_cast<uint4*>(out)[i] = pack8(a);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+image_to_uint8_kernel(const void* __restrict__ img, int in_is_fp32, uint8_t* __restrict__ out, int C, long long hw,
+                      long long total_px) {
+    for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < total_px;
+         px += (long long)gridDim.x * blockDim.x) {
+        const long long b = px / hw, r = px - b * hw;
+        for (int c = 0; c < C; ++c) {
+            const long long src = (b * C + c) * hw + r;
+            float x;
+            if (in_is_fp32) {
+                x = __ldg(reinterpret_cast<const float*>(img) + src);
+                x = fminf(fmaxf(x / 2.0f + 0.5f, 0.0f), 1.0f);
+                x = fminf(fmaxf(rintf(x * 255.0f), 0.0f), 255.0f);
+            } else {
+                x = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(img)[src]);
+                x = bf16_round(bf16_round(x / 2.0f) + 0.5f);
+                x = fminf(fmaxf(x, 0.0f), 1.0f);
+                x = fminf(fmaxf(rintf(bf16_round(x * 255.0f)), 0.0f), 255.0f);
+            }
+            out[px * C + c] = (uint8_t)x;
+        }
+    }
+}
+
 }  // namespace flite

@@ -252,6 +252,56 @@ int flite_cfg_euler(void* acc, int acc_is_fp32, const void* v_uncond, const void
     return 0;
 }
 
+int flite_apg_workspace_bytes(void) { return 4 * APG_BLOCKS * (int)sizeof(double); }
+
+int flite_apg_euler(void* acc, int acc_is_fp32, const void* v_uncond, const void* v_cond, float guidance, float dt,
+                    float orthogonal_threshold, void* lat_out, int64_t numel, void* workspace, void* stream) {
+    if (!acc || !v_cond || !v_uncond || !lat_out || !workspace) return fail(FLITE_ERR_INVALID, "apg_euler: null pointer");
+    if (numel <= 8 || numel % 8) return fail(FLITE_ERR_INVALID, "apg_euler: numel %lld must be a multiple of 8 greater than 8", (long long)numel);
+    if ((uintptr_t)workspace % 8) return fail(FLITE_ERR_INVALID, "apg_euler: workspace must be 8-byte aligned");
+    const long long n8 = numel / 8;
+    cudaStream_t s = (cudaStream_t)stream;
+    const __nv_bfloat16* u = (const __nv_bfloat16*)v_uncond;
+    const __nv_bfloat16* c = (const __nv_bfloat16*)v_cond;
+    double* ws = (double*)workspace;
+    const float gm1 = (float)((double)guidance - 1.0);
+    apg_dot_kernel<<<APG_BLOCKS, APG_THREADS, 0, s>>>(u, c, n8, ws);
+    LAUNCH_CHECK();
+    apg_orth_stats_kernel<<<APG_BLOCKS, APG_THREADS, 0, s>>>(u, c, n8, ws);
+    LAUNCH_CHECK();
+    apg_euler_kernel<<<APG_BLOCKS, APG_THREADS, 0, s>>>(acc, acc_is_fp32, u, c, gm1, dt, orthogonal_threshold,
+                                                         (__nv_bfloat16*)lat_out, n8, ws);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int flite_latent_unscale(const void* latents, void* out, float scaling_factor, float shift_factor, int64_t numel,
+                         void* stream) {
+    if (!latents || !out) return fail(FLITE_ERR_INVALID, "latent_unscale: null pointer");
+    if (numel <= 0 || numel % 8) return fail(FLITE_ERR_INVALID, "latent_unscale: numel must be a positive multiple of 8");
+    if (scaling_factor == 0.0f) return fail(FLITE_ERR_INVALID, "latent_unscale: scaling_factor is zero");
+    const long long n8 = numel / 8;
+    int blocks = (int)((n8 + 255) / 256);
+    const int cap = num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    latent_unscale_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)latents, (__nv_bfloat16*)out,
+                                                                    1.0f / scaling_factor, shift_factor, n8);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int flite_image_to_uint8(const void* decoded, int in_is_fp32, void* out_u8, int B, int C, int H, int W, void* stream) {
+    if (!decoded || !out_u8) return fail(FLITE_ERR_INVALID, "image_to_uint8: null pointer");
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    const long long hw = (long long)H * W, total = hw * B;
+    int blocks = (int)((total + 255) / 256);
+    const int cap = num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    image_to_uint8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(decoded, in_is_fp32, (uint8_t*)out_u8, C, hw, total);
+    LAUNCH_CHECK();
+    return 0;
+}
+
 int flite_rmsnorm_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w, int weight_mode,
                            const void* scale, const void* shift, int64_t ld_mod, int rows_per_sample, int rows, int d,
                            float eps, void* stream) {

@@ -73,6 +73,7 @@ def _chk(t: torch.Tensor, name: str, dtype=BF16, rows_contig=True):
         raise _lib.FliteError(f"{name}: innermost dimension must be contiguous")
 
 
+@_traced(lambda acc, *a, **k: f"cfg_euler {acc.numel()}")
 def cfg_euler(acc: torch.Tensor, v_uncond: Optional[torch.Tensor], v_cond: torch.Tensor, guidance: float,
               dt: float, lat_out: torch.Tensor, do_cfg: bool = True) -> None:
     """acc += dt * (u + g (c - u)); lat_out = bf16(acc).  f_lite/pipeline.py:290,296-297."""
@@ -90,6 +91,61 @@ def cfg_euler(acc: torch.Tensor, v_uncond: Optional[torch.Tensor], v_cond: torch
                                    v_cond.data_ptr(), float(guidance), float(dt), int(do_cfg), lat_out.data_ptr(),
                                    acc.numel(), _stream()), "cfg_euler")
     LAUNCHES[0] += 1
+
+
+_APG_WS = {}
+
+
+@_traced(lambda acc, *a, **k: f"apg_euler {acc.numel()}")
+def apg_euler(acc: torch.Tensor, v_uncond: torch.Tensor, v_cond: torch.Tensor, guidance: float, dt: float,
+              orthogonal_threshold: float, lat_out: torch.Tensor) -> None:
+    """Augmented Parallel Guidance combine + Euler update in three stream-ordered launches, no host sync.
+    f_lite/pipeline.py:276-287,296-297."""
+    lib = _lib.load()
+    for t, n in ((v_uncond, "v_uncond"), (v_cond, "v_cond"), (lat_out, "lat_out")):
+        _chk(t, n)
+    if acc.dtype not in (BF16, torch.float32):
+        raise _lib.FliteError("acc must be bf16 or fp32")
+    for t in (acc, v_uncond, v_cond, lat_out):
+        if not t.is_contiguous():
+            raise _lib.FliteError("apg_euler operands must be contiguous")
+    ws = _APG_WS.get(acc.device)
+    if ws is None:
+        ws = torch.empty(lib.flite_apg_workspace_bytes() // 8, dtype=torch.float64, device=acc.device)
+        _APG_WS[acc.device] = ws
+    _lib.check(lib.flite_apg_euler(acc.data_ptr(), int(acc.dtype == torch.float32), v_uncond.data_ptr(),
+                                   v_cond.data_ptr(), float(guidance), float(dt), float(orthogonal_threshold),
+                                   lat_out.data_ptr(), acc.numel(), ws.data_ptr(), _stream()), "apg_euler")
+    LAUNCHES[0] += 3
+
+
+def latent_unscale(latents: torch.Tensor, scaling_factor: float, shift_factor: float,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """latents / scaling_factor + shift_factor in bf16 (f_lite/pipeline.py:304)."""
+    lib = _lib.load()
+    _chk(latents, "latents")
+    if not latents.is_contiguous():
+        raise _lib.FliteError("latents must be contiguous")
+    if out is None:
+        out = torch.empty_like(latents)
+    _lib.check(lib.flite_latent_unscale(latents.data_ptr(), out.data_ptr(), float(scaling_factor), float(shift_factor),
+                                        latents.numel(), _stream()), "latent_unscale")
+    LAUNCHES[0] += 1
+    return out
+
+
+def image_to_uint8(decoded: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """decoded [B, C, H, W] bf16 or fp32 in [-1, 1] -> uint8 [B, H, W, C] (f_lite/pipeline.py:324-327)."""
+    lib = _lib.load()
+    if not decoded.is_cuda or decoded.dtype not in (BF16, torch.float32) or not decoded.is_contiguous():
+        raise _lib.FliteError("image_to_uint8: expected a contiguous CUDA bf16/fp32 [B, C, H, W] tensor")
+    B, C, H, W = decoded.shape
+    if out is None:
+        out = torch.empty((B, H, W, C), dtype=torch.uint8, device=decoded.device)
+    _lib.check(lib.flite_image_to_uint8(decoded.data_ptr(), int(decoded.dtype == torch.float32), out.data_ptr(), B, C,
+                                        H, W, _stream()), "image_to_uint8")
+    LAUNCHES[0] += 1
+    return out
 
 
 @_traced(lambda x, *a, **k: f"rmsnorm_modulate {tuple(x.shape)}")
@@ -128,6 +184,7 @@ def rope_qknorm_(buf: torch.Tensor, n_slots: int, cos: Optional[torch.Tensor], s
     LAUNCHES[0] += 1
 
 
+@_traced(lambda x, *a, **k: f"patch_embed {tuple(x.shape)}")
 def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, reg_tokens: torch.Tensor, patch: int,
                 out: Optional[torch.Tensor] = None, tok_offset: int = 0, tok_count: int = 0) -> torch.Tensor:
     lib = _lib.load()
@@ -148,6 +205,7 @@ def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, reg_t
     return out
 
 
+@_traced(lambda *a, **k: "timestep_embed")
 def timestep_embed(t_f32: torch.Tensor, t_is_bf16: bool, freqs: torch.Tensor, d: int,
                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
@@ -162,6 +220,7 @@ def timestep_embed(t_f32: torch.Tensor, t_is_bf16: bool, freqs: torch.Tensor, d:
     return out
 
 
+@_traced(lambda tok, *a, **k: f"unpatchify {tuple(tok.shape)}")
 def unpatchify(tok: torch.Tensor, B: int, C: int, H: int, W: int, patch: int, n_reg: int,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
@@ -174,6 +233,7 @@ def unpatchify(tok: torch.Tensor, B: int, C: int, H: int, W: int, patch: int, n_
     return out
 
 
+@_traced(lambda src, *a, **k: f"pack_context {tuple(src.shape)}")
 def pack_context(src: torch.Tensor, mask_f32: torch.Tensor):
     """src [B, Lc, d] bf16, mask [B, Lc] fp32 -> (packed [B*Lc, d] zero-padded, cu_seqlens int32 [B+1])."""
     lib = _lib.load()

@@ -111,17 +111,17 @@ def denoise(dit_model, latents, negative_embeds, prompt_embeds, mask=None, num_i
     t_all = torch.tensor([[t] * rows for t, _ in sched], dtype=latents.dtype).to(latents.device)
     for step, (t, dt) in enumerate(sched):
         t_tensor = t_all[step]
-        if apg and do_cfg:
-            # Augmented Parallel Guidance (pipeline.py:276-287): three global reductions -- not on the
-            # headline path; evaluated with torch ops on the kernel-produced velocities.
+        if apg and do_cfg and not split_cfg:
+            # Augmented Parallel Guidance (pipeline.py:276-287): the three global reductions and the update run on the
+            # device (flite_apg_euler), no host sync.
             out = dit_model(torch.cat([latents] * 2), context_input, mask_input, t_tensor)
-            uncond, cond = out.chunk(2)
-            dy, dd = cond, cond - uncond
-            par = (dy * dd).sum() / (dy * dy).sum() * dy
-            orth = dd - par
-            orth = orth * min(1, apg_config.orthogonal_threshold / orth.std())
-            v = dy + (guidance_scale - 1) * orth
-            ops.cfg_euler(acc, None, v.contiguous(), 1.0, dt, latents, do_cfg=False)
+            ops.apg_euler(acc, out[:b], out[b:], guidance_scale, dt, apg_config.orthogonal_threshold, latents)
+        elif apg and do_cfg:
+            import torch.distributed as dist
+            mine = dit_model(latents, context_input, mask_input, t_tensor)
+            out = torch.empty((2 * b,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+            dist.all_gather_into_tensor(out, mine.contiguous(), group=cfg_group)
+            ops.apg_euler(acc, out[:b], out[b:], guidance_scale, dt, apg_config.orthogonal_threshold, latents)
         else:
             out = denoise_step(dit_model, latents, acc, context_input, mask_input, t_tensor, dt, guidance_scale, do_cfg,
                                cfg_group=cfg_group if split_cfg else None)
@@ -255,13 +255,15 @@ class FLitePipeline:
         # pipeline.py:299-327 (decode + post-process); VAE is a "next" row, run through the caller's module
         scaling = getattr(self.vae.config, "scaling_factor", 0.18215) if hasattr(self.vae, "config") else 0.18215
         shift = getattr(self.vae.config, "shift_factor", 0) if hasattr(self.vae, "config") else 0
-        lat = latents / scaling + shift
+        lat = ops.latent_unscale(latents.contiguous(), scaling, shift)
         vae_dtype = self.vae.dtype if hasattr(self.vae, "dtype") else dtype
         decoded = self.vae.decode(lat.to(vae_dtype))
         decoded = decoded.sample if hasattr(decoded, "sample") else decoded
-        images = (decoded / 2 + 0.5).clamp(0, 1)
-        images = (images * 255).round().clamp(0, 255).to(torch.uint8).cpu()
+        if decoded.dtype not in (torch.bfloat16, torch.float32):
+            decoded = decoded.float()
+        images_hwc = ops.image_to_uint8(decoded.contiguous()).cpu()           # [B, H, W, C] uint8, PIL layout
+        images = images_hwc.permute(0, 3, 1, 2)                               # the reference's NCHW view
         if output_type == "pt":
             return FLitePipelineOutput(images=images)
         from PIL import Image
-        return FLitePipelineOutput(images=[Image.fromarray(img.permute(1, 2, 0).numpy()) for img in images])
+        return FLitePipelineOutput(images=[Image.fromarray(img.numpy()) for img in images_hwc])

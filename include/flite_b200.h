@@ -81,6 +81,23 @@ int flite_watchdog_status(unsigned int* code_out);
 int flite_cfg_euler(void* acc, int acc_is_fp32, const void* v_uncond, const void* v_cond, float guidance,
                     float dt, int do_cfg, void* lat_out, int64_t numel, void* stream);
 
+/* Sampler: Augmented Parallel Guidance combine + Euler update.           pipeline.py:276-287,296-297
+ *   dy = c; dd = c-u; par = (dy.dd)/(dy.dy)*dy (global sums over the whole tensor); orth = dd-par;
+ *   orth *= min(1, threshold/std(orth)); v = dy + (g-1)*orth; acc += dt*v; lat_out = bf16(acc)
+ *   every torch rounding point of the model dtype (bf16) is reproduced; the three global reductions are evaluated on
+ *   the device (3 stream-ordered launches, no host sync -- the reference syncs in `min(1, tensor)`).
+ *   workspace: flite_apg_workspace_bytes() bytes of device memory, 8-byte aligned, owned by the caller. */
+int flite_apg_workspace_bytes(void);
+int flite_apg_euler(void* acc, int acc_is_fp32, const void* v_uncond, const void* v_cond, float guidance, float dt,
+                    float orthogonal_threshold, void* lat_out, int64_t numel, void* workspace, void* stream);
+
+/* Pipeline tail.  latent_unscale: out = lat/scaling_factor + shift_factor (bf16)                 pipeline.py:304
+ *   image_to_uint8: (x/2+0.5).clamp(0,1)*255 -> round -> uint8, decoded [B,C,H,W] (bf16 or fp32) -> out [B,H,W,C]
+ *   (pipeline.py:324-327; the reference keeps NCHW and permutes each image on the host) */
+int flite_latent_unscale(const void* latents, void* out, float scaling_factor, float shift_factor, int64_t numel,
+                         void* stream);
+int flite_image_to_uint8(const void* decoded, int in_is_fp32, void* out_u8, int B, int C, int H, int W, void* stream);
+
 /* y = RMSNorm(x)[*w] [*(1+scale[s]) + shift[s]], s = row / rows_per_sample.   model.py:238,283-284,292-293,299-300,437,579-580
  *   weight_mode 0 none | 1 Liger "llama" casting | 2 reference RMSNorm (fp32 weight multiply)
  *   scale/shift may be NULL (no modulation); they index a [B, ld_mod] modulation matrix */

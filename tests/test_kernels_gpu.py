@@ -409,3 +409,65 @@ def test_attention_staged_output_stores_bit_equal(variant):
         lib.flite_set_tuning(7, 0)
     assert torch.equal(staged[:sum(q_lens)], plain)
     assert bool((staged[sum(q_lens):] == 7.0).all())
+
+
+# ----------------------------------------------------------------------------- sampler / pipeline tail
+def _apg_torch(acc, u, c, g, dt, thr):
+    """f_lite/pipeline.py:276-287,296 with torch ops in the tensors' dtype (the reference, run on this device)."""
+    from oracle import sampler_oracle
+    v = sampler_oracle.apg_combine(u, c, g, thr)
+    return acc + dt * v
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 32, 32), (1, 16, 128, 128), (3, 16, 112, 168)])
+@pytest.mark.parametrize("thr", [0.03, 5.0])
+def test_apg_euler_matches_reference_ops(shape, thr):
+    """flite_apg_euler vs the reference's torch op sequence.  The three global reductions are summed in a different
+    order (fp64 block partials vs torch's fp32 tree), so a bf16 scalar may differ by one ulp: tolerance 1e-2 rel-L2 on
+    the update, and the update must be far closer to the reference than plain CFG is (the kernel implements APG)."""
+    from flite_b200 import ops
+    u, c = rnd(*shape, seed=1), rnd(*shape, scale=1.0, seed=2) * 0.7 + rnd(*shape, seed=1) * 0.5
+    acc0 = rnd(*shape, seed=3)
+    g, dt = 6.0, 0.0625
+    ref = _apg_torch(acc0, u, c, g, dt, thr)
+    acc, lat = acc0.clone(), torch.empty_like(acc0)
+    ops.apg_euler(acc, u, c, g, dt, thr, lat)
+    assert torch.equal(acc, lat)
+    d_ref = (ref - acc0).float()
+    r = ((acc - acc0).float() - d_ref).norm() / d_ref.norm()
+    plain = (dt * (u + g * (c - u))).float()
+    assert r.item() <= 1e-2, r.item()
+    assert (plain - d_ref).norm() / d_ref.norm() > 10 * max(r.item(), 1e-4)
+    # fp32 accumulator (train.py sample_images semantics)
+    acc32, lat32 = acc0.float(), torch.empty_like(acc0)
+    ops.apg_euler(acc32, u, c, g, dt, thr, lat32)
+    from oracle import sampler_oracle
+    ref32 = acc0.float() + dt * sampler_oracle.apg_combine(u, c, g, thr).float()        # train.py:599 accumulation
+    assert rel(acc32 - acc0.float(), ref32 - acc0.float()) <= 1e-2 and torch.equal(lat32, acc32.bfloat16())
+
+
+def test_apg_euler_degenerate_inputs():
+    """cond == uncond: dd = 0, orth = -coef*dy = 0, std = 0 -> threshold/std = inf -> scale 1; v = dy (no NaNs)."""
+    from flite_b200 import ops
+    c = rnd(1, 16, 32, 32, seed=4)
+    acc, lat = torch.zeros_like(c), torch.empty_like(c)
+    ops.apg_euler(acc, c.clone(), c, 6.0, 1.0, 0.03, lat)
+    assert torch.isfinite(acc.float()).all() and torch.equal(acc, c)
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 32, 32), (2, 16, 128, 128)])
+def test_latent_unscale_bit_exact(shape):
+    from flite_b200 import ops
+    lat = rnd(*shape, seed=5)
+    assert torch.equal(ops.latent_unscale(lat, 0.3611, 0.1159), lat / 0.3611 + 0.1159)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape", [(1, 3, 256, 256), (2, 3, 64, 96), (1, 1, 8, 8), (1, 4, 17, 5)])
+def test_image_to_uint8_bit_exact(dtype, shape):
+    """(x/2+0.5).clamp(0,1)*255 -> round -> uint8 (pipeline.py:324-326) + the NCHW->NHWC permute of pipeline.py:327."""
+    from flite_b200 import ops
+    x = (torch.randn(shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(6)) * 0.8).to(dtype)
+    x.view(-1)[:6] = torch.tensor([-1.0, 1.0, 0.0, -3.0, 3.0, 0.00196], device=DEV).to(dtype)[: min(6, x.numel())]
+    ref = ((x / 2 + 0.5).clamp(0, 1) * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    assert torch.equal(ops.image_to_uint8(x), ref)
