@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(64 + 128 * kWG, 1)
 attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
     const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
+    pdl_launch_dependents();   // PDL: the next kernel may be scheduled as SMs drain; it waits for this grid to finish
+    pdl_wait();                // q/k/v (and cu_seqlens) come from earlier kernels of the stream
     const int q_beg = p.cu_q[b], q_len = p.cu_q[b + 1] - q_beg;
     if ((qt & ~1) * 128 >= q_len) return;  // uniform for the whole cluster, before any barrier / TMEM allocation
     const int k_beg = p.cu_k[b], k_len = p.cu_k[b + 1] - k_beg;

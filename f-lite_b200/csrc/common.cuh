@@ -18,6 +18,14 @@ namespace flite {
 // ------------------------------------------------------------------------------------------
 __device__ unsigned int g_flite_abort = 0;   // 0 = ok, else (tag << 16 | blockIdx.x & 0xffff)
 
+// Programmatic dependent launch (PDL): kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while the previous kernel of the stream is still draining; pdl_wait() blocks until that kernel has
+// completed and its memory is visible (a no-op for a normal launch), pdl_launch_dependents() lets the NEXT kernel's
+// CTAs be scheduled as SMs free up.  Rule used throughout: nothing produced by an earlier kernel is read (and nothing
+// is written) before pdl_wait(); data rewritten inside the hot loop (residual stream) is read with ld.global.cg.
+FLITE_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+FLITE_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 FLITE_DEVICE uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

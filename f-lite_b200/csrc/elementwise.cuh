@@ -74,13 +74,15 @@ rmsnorm_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv
                         long long ldy, const __nv_bfloat16* __restrict__ w, int weight_mode,
                         const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift,
                         long long ld_mod, int rows_per_sample, int rows, int d, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();                 // x is the previous kernel's output (PDL launch)
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
     const int nchunk = d >> 3;  // 16-byte chunks per row
     float ssq = 0.f;
-    for (int c = lane; c < nchunk; c += 32) ssq += ssq_chunk(__ldg(xr + c));
+    for (int c = lane; c < nchunk; c += 32) ssq += ssq_chunk(__ldcg(xr + c));
     ssq = warp_sum(ssq);
     const float rstd = rsqrtf(ssq / (float)d + eps);
     const bool mod = scale != nullptr;
@@ -91,7 +93,7 @@ rmsnorm_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv
         const uint4 wv = weight_mode != 0 ? __ldg(reinterpret_cast<const uint4*>(w) + c) : z;
         const uint4 scv = mod ? __ldg(reinterpret_cast<const uint4*>(scale + s) + c) : z;
         const uint4 shv = mod ? __ldg(reinterpret_cast<const uint4*>(shift + s) + c) : z;
-        yr[c] = norm_mod_chunk(__ldg(xr + c), rstd, wv, weight_mode, mod, scv, shv);
+        yr[c] = norm_mod_chunk(__ldcg(xr + c), rstd, wv, weight_mode, mod, scv, shv);
     }
 }
 
@@ -103,6 +105,8 @@ rmsnorm_modulate_reg_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, 
                             long long ldy, const __nv_bfloat16* __restrict__ w, int weight_mode,
                             const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift,
                             long long ld_mod, int rows_per_sample, int rows, int d, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -112,7 +116,7 @@ rmsnorm_modulate_reg_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, 
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
         const int c = lane + 32 * i;
-        v[i] = (c < nchunk) ? __ldg(xr + c) : make_uint4(0, 0, 0, 0);
+        v[i] = (c < nchunk) ? __ldcg(xr + c) : make_uint4(0, 0, 0, 0);
     }
     float ssq = 0.f;
 #pragma unroll
@@ -132,6 +136,65 @@ rmsnorm_modulate_reg_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, 
             const uint4 shv = mod ? __ldg(reinterpret_cast<const uint4*>(shift + s) + c) : z;
             yr[c] = norm_mod_chunk(v[i], rstd, wv, weight_mode, mod, scv, shv);
         }
+    }
+}
+
+// Streaming variant (FLITE_TUNE_RMSNORM_KERNEL = 3): persistent warps, one row per warp per iteration, the row is read
+// ONCE into registers and the NEXT row's loads are issued before the current row is reduced and written, so loads,
+// math and stores of neighbouring rows overlap inside every warp (the one-shot kernels above run load / math / store
+// phases in lock step across the whole grid).  The host sizes the grid so that every warp gets the same row count.
+template <int MAXC>
+__global__ void __launch_bounds__(256, (MAXC <= 4) ? 2 : 1)
+rmsnorm_modulate_stream_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
+                               long long ldy, const __nv_bfloat16* __restrict__ w, int weight_mode,
+                               const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift,
+                               long long ld_mod, int rows_per_sample, int rows, int d, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * 8;
+    const int nchunk = d >> 3;
+    const bool mod = scale != nullptr;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    uint4 cur[MAXC], nxt[MAXC];
+    if (row < rows) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            cur[i] = (c < nchunk) ? __ldcg(xr + c) : z;
+        }
+    }
+    for (; row < rows; row += nwarps) {
+        const int nrow = row + nwarps;
+        if (nrow < rows) {
+            const uint4* xn = reinterpret_cast<const uint4*>(x + (long long)nrow * ldx);
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i) {
+                const int c = lane + 32 * i;
+                nxt[i] = (c < nchunk) ? __ldcg(xn + c) : z;
+            }
+        }
+        float ssq = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) ssq += ssq_chunk(cur[i]);
+        ssq = warp_sum(ssq);
+        const float rstd = rsqrtf(ssq / (float)d + eps);
+        const long long s = (long long)(row / rows_per_sample) * ld_mod;
+        uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nchunk) {
+                const uint4 wv = weight_mode != 0 ? __ldg(reinterpret_cast<const uint4*>(w) + c) : z;
+                const uint4 scv = mod ? __ldg(reinterpret_cast<const uint4*>(scale + s) + c) : z;
+                const uint4 shv = mod ? __ldg(reinterpret_cast<const uint4*>(shift + s) + c) : z;
+                yr[c] = norm_mod_chunk(cur[i], rstd, wv, weight_mode, mod, scv, shv);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) cur[i] = nxt[i];
     }
 }
 

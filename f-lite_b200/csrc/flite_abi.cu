@@ -22,7 +22,7 @@ using namespace flite;
 namespace {
 
 thread_local char g_err[512] = "";
-int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // FLITE_TUNE_* knobs (A/B switches for benchmarking)
+int g_tuning[16] = {0};   // FLITE_TUNE_* knobs (A/B switches for benchmarking)
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -123,6 +123,24 @@ int num_sms() {
     return n;
 }
 
+// Launch attributes of the hot-loop kernels: optional cluster dimension + programmatic dependent launch (PDL).
+int fill_launch_attrs(cudaLaunchAttribute* attr, int cluster_x) {
+    int n = 0;
+    if (cluster_x > 0) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (g_tuning[FLITE_TUNE_PDL] == 1) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    return n;
+}
+
 template <int kCtaGroup, int BLOCK_N, int kStages, int kEpi>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, GemmParams p,
                 cudaStream_t stream) {
@@ -174,13 +192,9 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = (kEpi == EPI_QKV_ROPE && p.stage_stores) ? S::TOTAL_STAGED : S::TOTAL;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCtaGroup;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = fill_launch_attrs(attr, kCtaGroup);
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbh, p));
     return 0;
 }
@@ -209,7 +223,7 @@ int flite_abi_version(void) { return FLITE_ABI_VERSION; }
 const char* flite_last_error(void) { return g_err; }
 
 int flite_set_tuning(int key, int value) {
-    if (key < 0 || key >= 8) return fail(FLITE_ERR_INVALID, "set_tuning: unknown key %d", key);
+    if (key < 0 || key >= 16) return fail(FLITE_ERR_INVALID, "set_tuning: unknown key %d", key);
     g_tuning[key] = value;
     return 0;
 }
@@ -312,11 +326,44 @@ int flite_rmsnorm_modulate(const void* x, int64_t ldx, void* y, int64_t ldy, con
     if (rows <= 0) return 0;
     if (rows_per_sample <= 0) rows_per_sample = rows;
     auto launch = [&](auto kern, int rows_per_block, int threads) {
-        kern<<<(rows + rows_per_block - 1) / rows_per_block, threads, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const __nv_bfloat16*)w, weight_mode,
-            (const __nv_bfloat16*)scale, (const __nv_bfloat16*)shift, ld_mod, rows_per_sample, rows, d, eps);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((rows + rows_per_block - 1) / rows_per_block);
+        cfg.blockDim = dim3(threads);
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[2];
+        cfg.attrs = attr;
+        cfg.numAttrs = fill_launch_attrs(attr, 0);
+        const long long ldx_ = ldx, ldy_ = ldy, ld_mod_ = ld_mod;
+        cudaLaunchKernelEx(&cfg, kern, (const __nv_bfloat16*)x, ldx_, (__nv_bfloat16*)y, ldy_, (const __nv_bfloat16*)w,
+                           weight_mode, (const __nv_bfloat16*)scale, (const __nv_bfloat16*)shift, ld_mod_,
+                           rows_per_sample, rows, d, eps);
     };
-    const int mode = g_tuning[FLITE_TUNE_RMSNORM_KERNEL];   // 0 auto (two-pass), 1 two-pass, 2 register-resident
+    const int mode = g_tuning[FLITE_TUNE_RMSNORM_KERNEL];   // 0 auto (two-pass), 1 two-pass, 2 register-resident, 3 streaming
+    if (mode == 3 && d <= 8 * 32 * 16) {
+        // persistent warps: 1 (wide rows) or 2 blocks x 8 warps per SM; shrink the grid so that every warp gets the same
+        // number of rows
+        const int slots = num_sms() * (d <= 8 * 32 * 4 ? 2 : 1) * 8;
+        const int iters = (rows + slots - 1) / slots;
+        const int blocks = (rows + 8 * iters - 1) / (8 * iters);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks);
+        cfg.blockDim = dim3(256);
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[2];
+        cfg.attrs = attr;
+        cfg.numAttrs = fill_launch_attrs(attr, 0);
+        const long long ldx_ = ldx, ldy_ = ldy, ld_mod_ = ld_mod;
+        auto go = [&](auto kern) {
+            cudaLaunchKernelEx(&cfg, kern, (const __nv_bfloat16*)x, ldx_, (__nv_bfloat16*)y, ldy_, (const __nv_bfloat16*)w,
+                               weight_mode, (const __nv_bfloat16*)scale, (const __nv_bfloat16*)shift, ld_mod_,
+                               rows_per_sample, rows, d, eps);
+        };
+        if (d <= 8 * 32 * 4) go(rmsnorm_modulate_stream_kernel<4>);
+        else if (d <= 8 * 32 * 12) go(rmsnorm_modulate_stream_kernel<12>);
+        else go(rmsnorm_modulate_stream_kernel<16>);
+        LAUNCH_CHECK();
+        return 0;
+    }
     if (mode == 2 && d <= 8 * 32 * 4) launch(rmsnorm_modulate_reg_kernel<4>, 8, 256);
     else if (mode == 2 && d <= 8 * 32 * 12) launch(rmsnorm_modulate_reg_kernel<12>, 8, 256);
     else if (mode == 2 && d <= 8 * 32 * 16) launch(rmsnorm_modulate_reg_kernel<16>, 8, 256);
@@ -606,13 +653,9 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
     cfg.blockDim = dim3(one_wg ? 192 : 320);
     cfg.dynamicSmemBytes = ATT_SMEM;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = fill_launch_attrs(attr, 2);
     switch (variant) {
         case FLITE_ATTN_2CTA_1WG: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<1, false>, tq, tk, tv, p)); break;
         case FLITE_ATTN_2CTA_2WG: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<2, false>, tq, tk, tv, p)); break;

@@ -123,6 +123,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // PDL: barrier init / TMEM allocation above overlap the previous kernel's tail; no global access before this point
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int num_m_tiles = (p.M + TILE_M - 1) / TILE_M;
     const int num_n_tiles = p.N / BLOCK_N;
@@ -273,7 +276,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             const uint4* gp = reinterpret_cast<const uint4*>(gate_row + col);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                uint4 v = __ldg(rp + j);
+                                uint4 v = __ldcg(rp + j);   // residual stream: rewritten every GEMM, keep it out of L1
                                 res_p[4 * j] = v.x; res_p[4 * j + 1] = v.y; res_p[4 * j + 2] = v.z; res_p[4 * j + 3] = v.w;
                                 uint4 g = __ldg(gp + j);
                                 gate_p[4 * j] = g.x; gate_p[4 * j + 1] = g.y; gate_p[4 * j + 2] = g.z; gate_p[4 * j + 3] = g.w;

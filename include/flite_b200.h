@@ -56,13 +56,15 @@ extern "C" {
 #define FLITE_ATTN_QTMEM_2WG 8
 
 /* tuning knobs (A/B switches used by the benchmarks; defaults are the measured best) */
-#define FLITE_TUNE_RMSNORM_KERNEL 0  /* 0 auto | 1 two-pass | 2 register-resident */
+#define FLITE_TUNE_RMSNORM_KERNEL 0  /* 0 auto | 1 two-pass | 2 register-resident | 3 streaming (persistent warps, next-row prefetch) */
 #define FLITE_TUNE_ATTN_VARIANT 1    /* default attention variant when the call passes FLITE_ATTN_AUTO */
 #define FLITE_TUNE_GEMM_VARIANT 2    /* default GEMM variant when the call passes FLITE_GEMM_AUTO (0 = heuristic) */
 #define FLITE_TUNE_ATTN_DEBUG 3      /* profiling experiments only: bit0 skip softmax math, bit1 skip K/V reloads */
 #define FLITE_TUNE_GEMM_TAIL_SPLIT 4 /* 0 = run a last partial wave as half-width tiles (default), 1 = off */
 #define FLITE_TUNE_QKV_STAGED_STORES 6 /* 1 = QKV epilogue stores whole row segments via a shared-memory transpose (always on for peer stores) */
 #define FLITE_TUNE_ATTN_STAGED_STORES 7 /* 1 = 2-CTA attention stores whole output rows via a shared-memory transpose (always on for peer stores) */
+#define FLITE_TUNE_PDL 8             /* 1 = GEMM / attention / rmsnorm kernels use programmatic dependent launch; default 0 = off:
+                                        measured 1 % SLOWER at C2 (profiles/r1e_ab_pdl.json) -- the step is power-capped, idle gaps are free */
 #define FLITE_TUNE_GEMM_BAND 5       /* 0 = L2-aware band rasterisation for large M (default), 1 = single band */
 int flite_set_tuning(int key, int value);
 

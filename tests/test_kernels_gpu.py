@@ -471,3 +471,26 @@ def test_image_to_uint8_bit_exact(dtype, shape):
     x.view(-1)[:6] = torch.tensor([-1.0, 1.0, 0.0, -3.0, 3.0, 0.00196], device=DEV).to(dtype)[: min(6, x.numel())]
     ref = ((x / 2 + 0.5).clamp(0, 1) * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
     assert torch.equal(ops.image_to_uint8(x), ref)
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("rows,d,B", [(2 * 272, 512, 2), (2 * 4112, 3072, 2), (5, 256, 1), (37, 4096, 1), (3 * 5000, 1024, 3)])
+def test_rmsnorm_kernel_variants_bit_equal(kernel, rows, d, B):
+    """FLITE_TUNE_RMSNORM_KERNEL 1 (two-pass) / 2 (register-resident) / 3 (streaming, persistent warps with next-row
+    prefetch) must produce identical bits (same arithmetic, different schedule)."""
+    from flite_b200 import _lib, ops
+    x = rnd(rows, d, seed=1)
+    w = (1 + 0.1 * torch.randn(d, device=DEV)).bfloat16()
+    mod = rnd(B, 9 * d, scale=0.5, seed=2)
+    L = rows // B
+    base = ops.rmsnorm_modulate(x, w, 1, mod[:, d:2 * d], mod[:, :d], rows_per_sample=L)
+    lib = _lib.load()
+    lib.flite_set_tuning(0, kernel)
+    try:
+        y = torch.full((rows + 3, d), 7.0, device=DEV, dtype=torch.bfloat16)
+        ops.rmsnorm_modulate(x, w, 1, mod[:, d:2 * d], mod[:, :d], rows_per_sample=L, out=y[:rows])
+        y2 = ops.rmsnorm_modulate(x, w, 2)
+    finally:
+        lib.flite_set_tuning(0, 0)
+    assert torch.equal(y[:rows], base) and bool((y[rows:] == 7.0).all())
+    assert torch.equal(y2, ops.rmsnorm_modulate(x, w, 2))

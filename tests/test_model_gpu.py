@@ -271,3 +271,29 @@ def test_pipeline_call_decodes_to_uint8_images(golden_dir):
     assert torch.equal(out, ref)
     pil = pipe(generator=torch.Generator(device=DEV).manual_seed(3), **kw).images
     assert pil[0].size == (256, 256) and pil[0].mode == "RGB"
+
+
+def test_programmatic_dependent_launch_is_bit_identical():
+    """FLITE_TUNE_PDL = 1 (opt-in): the GEMM / attention / rmsnorm kernels start under programmatic dependent launch
+    (their prologue overlaps the previous kernel's tail).  Several denoise steps at the 10B width with changing
+    timesteps must give exactly the bits of the fully serialised launches (stale-read / ordering check)."""
+    import flite_b200
+    from flite_b200 import _lib
+    from oracle import synth
+    cfg = dict(synth.ARCH_10B, depth=3)
+    sd = synth.make_state_dict(cfg, 0, device=DEV)
+    m = _model(cfg, sd)
+    m.hoist_context = False
+    x, ctx, mask = synth.make_inputs(cfg, 1, 1024, 1024, 256, valid_len=[200], device=DEV)
+    lat0, neg, pos = x.bfloat16(), ctx[:1].bfloat16(), ctx[1:].bfloat16()
+    lib = _lib.load()
+    outs = []
+    for on in (0, 1, 1):
+        lib.flite_set_tuning(8, on)
+        try:
+            outs.append(flite_b200.denoise(m, lat0, neg, pos, mask, 5, 6.0))
+        finally:
+            lib.flite_set_tuning(8, 0)
+    _lib.watchdog_ok()
+    assert torch.isfinite(outs[0].float()).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
