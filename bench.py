@@ -325,6 +325,13 @@ def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 "flops_per_launch": dom_flops, "avg_launch_ms": avg, "launches_timed": len(dom_ms),
                 "share_of_step": avg * len(dom_ms) / args.steps / ms_step, "traffic": None}
+        if (M, N, K) == (8224, 24576, 3072):
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
+            # committed as profiles/r1e_ncu_full_top_kernels.csv (518.6 MB + 202.1 MB per launch; the algorithmic
+            # 2(MK + NK + MN/2) = 404 MB: W streams once per 32 MB band of A)
+            roof["traffic"] = 720.6e6
+            roof["traffic_unit"] = "bytes of DRAM traffic per launch (ncu, profiles/r1e_ncu_full_top_kernels.csv)"
+            roof["algorithmic_bytes_per_launch"] = 2.0 * (M * K + N * K + M * N // 2)
 
     # ---- end-to-end run: host (pinned) buffers in, host buffer out, every step
     lat_h = lat0.cpu().pin_memory()
