@@ -157,9 +157,20 @@ class FLitePipeline:
     def progress_bar(self, it):
         return it
 
+    # the system turn the reference puts in front of every caption (f_lite/pipeline.py:105); F Lite was trained with it,
+    # so it is part of the text-conditioning interface, not a tunable
+    SYSTEM_PROMPT = (
+        "You are a text-to-image generation model engineered to transform user-provided textual captions directly into "
+        "high-quality, visually rich image tokens. Your core objective is to generate the best possible, highest-fidelity "
+        "image that creatively interprets and expands upon the user's intent while maintaining strong semantic alignment "
+        "with the original caption. You are designed for maximum visual quality, artistic flair, and implicit adherence to "
+        "best practices in image generation (e.g., proper anatomy, clear focus, compelling composition), ensuring a "
+        "stunning visual result from even concise descriptions.")
+
     def _convert_caption_to_messages(self, caption: str) -> str:
-        """pipeline.py:105-124 (chat template around the caption)."""
-        messages = [{"role": "user", "content": [{"type": "text", "text": caption}]}]
+        """pipeline.py:104-124 (system turn + user caption through the processor's chat template)."""
+        messages = [{"role": "system", "content": self.SYSTEM_PROMPT},
+                    {"role": "user", "content": [{"type": "text", "text": caption}]}]
         return self.processor.apply_chat_template(messages, tokenize=False, add_generation_prompt=True)
 
     def encode_prompt(self, prompt, negative_prompt=None, device=None, dtype=None, max_sequence_length=512,

@@ -71,6 +71,23 @@ def main():
                os.path.join(OUT, "tiny_256_sampler.pt"))
     print("sampler: pipeline-vs-train rel-L2", ((lat - lat2).norm() / lat.norm()).item())
 
+    # the reference's own FLitePipeline.__call__ end to end (pipeline.py:188-331): schedule, CFG / APG combine,
+    # accumulator dtype, latent unscale, post-process -- with stand-ins for the three third-party models
+    from . import ref_pipeline_shim
+    rec = case_recipe("tiny_256")
+    sd, _, ctx, _, _ = build_case(rec)
+    out = dict(recipe=rec, seed=77, steps=4, guidance=6.0, apg_threshold=0.03, height=256, width=256)
+    for dtype, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        for apg, atag in ((None, "cfg"), (0.03, "apg")):
+            z, imgs, proc = ref_pipeline_shim.run_reference_pipeline(rec["cfg"], sd, ctx[rec["batch"]:], dtype, 77, 256, 256,
+                                                                     4, 6.0, apg)
+            out[f"decode_input_{atag}_{tag}"] = z
+            if apg is None:
+                out[f"images_{atag}_{tag}"] = imgs
+            print("pipeline", tag, atag, "decode-input std", z.float().std().item(), "image mean", imgs.float().mean().item())
+    out["chat_messages"] = proc.templated[-1]
+    torch.save(out, os.path.join(OUT, "tiny_256_pipeline.pt"))
+
 
 if __name__ == "__main__":
     main()

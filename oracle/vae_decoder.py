@@ -90,6 +90,13 @@ def decode_to_image(dec: Decoder, latents: torch.Tensor, gain: float = 1.0) -> t
     return (x / 2 + 0.5).clamp(0, 1)
 
 
+def toy_decode(z: torch.Tensor) -> torch.Tensor:
+    """Deterministic, cheap stand-in for ``AutoencoderKL.decode`` used by the pipeline golden fixture
+    (oracle/ref_pipeline_shim.py): 3 channel mixes of the latent, 8x nearest upsampling."""
+    mix = torch.stack([z[:, i::3].mean(1) for i in range(3)], 1)
+    return F.interpolate(mix * 0.9, scale_factor=8, mode="nearest")
+
+
 def psnr(a: torch.Tensor, b: torch.Tensor) -> float:
     mse = (a.float() - b.float()).pow(2).mean().item()
     return float("inf") if mse == 0 else 10.0 * torch.log10(torch.tensor(1.0 / mse)).item()

@@ -297,3 +297,44 @@ def test_programmatic_dependent_launch_is_bit_identical():
     _lib.watchdog_ok()
     assert torch.isfinite(outs[0].float()).all()
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
+@pytest.mark.parametrize("mode", ["cfg", "apg"])
+def test_pipeline_call_vs_reference_pipeline_golden(mode, golden_dir):
+    """flite_b200.FLitePipeline.__call__ against the fixture written by the UNMODIFIED reference FLitePipeline.__call__
+    (tests/golden/tiny_256_pipeline.pt): same CPU generator seed, same embeddings, toy VAE.  Checks the decode input
+    (trajectory + latent unscale) against the reference's bf16 run and the uint8 image."""
+    import flite_b200
+    from types import SimpleNamespace
+    from oracle import vae_decoder
+    from oracle.make_golden import build_case
+    g = torch.load(os.path.join(golden_dir, "tiny_256_pipeline.pt"), weights_only=False)
+    rec = g["recipe"]
+    sd, _, ctx, _, _ = build_case(rec, device=DEV)
+    m = _model(rec["cfg"], sd)
+
+    class VAE:
+        config = SimpleNamespace(scaling_factor=vae_decoder.SCALING_FACTOR, shift_factor=vae_decoder.SHIFT_FACTOR)
+        dtype = torch.bfloat16
+        seen = []
+
+        def decode(self, z):
+            self.seen.append(z)
+            return SimpleNamespace(sample=vae_decoder.toy_decode(z))
+
+    vae = VAE()
+    pipe = flite_b200.FLitePipeline(m, vae, None, None)
+    apg = flite_b200.APGConfig(enabled=True, orthogonal_threshold=g["apg_threshold"]) if mode == "apg" else None
+    out = pipe(prompt=None, height=g["height"], width=g["width"], num_inference_steps=g["steps"],
+               guidance_scale=g["guidance"], generator=torch.Generator().manual_seed(g["seed"]), apg_config=apg,
+               prompt_embeds=ctx[rec["batch"]:].bfloat16(), output_type="pt").images
+    z = vae.seen[-1].float().cpu()
+    # (the fixture's fp32 run starts from different noise -- randn in fp32 vs bf16 -- so only the bf16 run is comparable)
+    r_bf16 = rel(z, g[f"decode_input_{mode}_bf16"])
+    print(f"{mode}: decode input vs the reference pipeline's bf16 run {r_bf16:.2e}")
+    assert r_bf16 <= 3e-2
+    if mode == "cfg":
+        ref_img = g["images_cfg_bf16"].permute(0, 3, 1, 2)
+        diff = (out.int() - ref_img.int()).abs().float()
+        print("uint8 image: mean |diff|", diff.mean().item(), "max", diff.max().item())
+        assert diff.mean().item() < 1.0
