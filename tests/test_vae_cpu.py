@@ -1,0 +1,68 @@
+"""CPU: the product-side VAE decoder (torch / library convs) against the oracle restatement, and its
+diffusers-compatible parameter names."""
+import torch
+
+from oracle import vae_decoder
+
+
+def _map_to_oracle(sd):
+    """flite_b200.vae (diffusers names) -> oracle/vae_decoder.py (Sequential indices)."""
+    out = {}
+    up_idx = 0
+    for k, v in sd.items():
+        k = k[len("decoder."):]
+        if k.startswith("mid_block.resnets.0."):
+            out["mid.0." + k[len("mid_block.resnets.0."):]] = v
+        elif k.startswith("mid_block.resnets.1."):
+            out["mid.2." + k[len("mid_block.resnets.1."):]] = v
+        elif k.startswith("mid_block.attentions.0."):
+            r = k[len("mid_block.attentions.0."):]
+            r = (r.replace("group_norm.", "norm.").replace("to_q.", "q.").replace("to_k.", "k.").replace("to_v.", "v.")
+                  .replace("to_out.0.", "o."))
+            out["mid.1." + r] = v
+        elif k.startswith("up_blocks."):
+            _, i, kind, j, rest = k.split(".", 4)
+            i, j = int(i), int(j)
+            base = i * 5                       # 3 resnets + upsample + conv per block in the oracle's Sequential
+            if kind == "resnets":
+                out[f"up.{base + j}." + rest.replace("conv_shortcut.", "shortcut.")] = v
+            else:                              # upsamplers.0.conv.*
+                out[f"up.{base + 4}." + rest[len("conv."):]] = v
+        elif k.startswith("conv_norm_out."):
+            out["norm_out." + k[len("conv_norm_out."):]] = v
+        else:
+            out[k] = v
+    return out
+
+
+def test_decoder_matches_oracle_restatement_fp32():
+    from flite_b200 import vae
+    torch.manual_seed(0)
+    m = vae.AutoencoderKL().eval()
+    ref = vae_decoder.Decoder().eval()
+    missing, unexpected = ref.load_state_dict(_map_to_oracle(m.state_dict()), strict=True)
+    assert not missing and not unexpected
+    z = torch.randn(2, 16, 8, 8)
+    with torch.no_grad():
+        a, b = m.decode(z).sample, ref(z)
+    assert a.shape == (2, 3, 64, 64)
+    assert ((a - b).norm() / b.norm()).item() <= 1e-5
+    m.enable_slicing()
+    assert torch.allclose(m.decode(z).sample, a, atol=1e-5)
+    assert m.config.scaling_factor == vae_decoder.SCALING_FACTOR and m.config.shift_factor == vae_decoder.SHIFT_FACTOR
+
+
+def test_decoder_parameter_names_follow_diffusers():
+    from flite_b200 import vae
+    keys = set(vae.AutoencoderKL().state_dict())
+    for k in ("decoder.conv_in.weight", "decoder.mid_block.resnets.0.norm1.weight",
+              "decoder.mid_block.attentions.0.group_norm.weight", "decoder.mid_block.attentions.0.to_q.weight",
+              "decoder.mid_block.attentions.0.to_out.0.bias", "decoder.up_blocks.0.resnets.2.conv2.weight",
+              "decoder.up_blocks.2.resnets.0.conv_shortcut.weight", "decoder.up_blocks.0.upsamplers.0.conv.weight",
+              "decoder.up_blocks.3.resnets.0.conv_shortcut.weight", "decoder.conv_norm_out.weight",
+              "decoder.conv_out.bias"):
+        assert k in keys, k
+    assert "decoder.up_blocks.3.upsamplers.0.conv.weight" not in keys        # last block does not upsample
+    assert "decoder.up_blocks.1.resnets.0.conv_shortcut.weight" not in keys  # 512 -> 512
+    n = sum(v.numel() for v in vae.AutoencoderKL().state_dict().values())
+    assert 49_000_000 < n < 50_500_000                                       # FLUX VAE decoder: ~49.5 M parameters
