@@ -234,14 +234,64 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int n0 = n_blk * BLOCK_N + (half > 0 ? BLOCK_N / 2 : 0);
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
+            // EPI_GATED_RES: the residual row slice, the per-sample gate and the bias do not depend on the accumulator;
+            // chunk c+1's loads are issued before chunk c is combined, and the first chunk's loads are issued before
+            // the wait for the accumulator itself, so their latency hides behind the mainloop / the previous chunk.
+            uint4 res_n[4], gate_n[4], bias_n[4];
+            const __nv_bfloat16* gate_row = nullptr;
+            const __nv_bfloat16* res_row = nullptr;
+            auto prefetch = [&](int col) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    res_n[j] = row_ok ? __ldcg(reinterpret_cast<const uint4*>(res_row + col) + j) : make_uint4(0, 0, 0, 0);
+                    gate_n[j] = __ldg(reinterpret_cast<const uint4*>(gate_row + col) + j);
+                    bias_n[j] = p.bias != nullptr ? __ldg(reinterpret_cast<const uint4*>(p.bias + col) + j)
+                                                  : make_uint4(0, 0, 0, 0);
+                }
+            };
+            if constexpr (kEpi == EPI_GATED_RES) {
+                gate_row = p.gate + (long long)((row_ok ? row : 0) / p.rows_per_sample) * p.ld_gate;
+                res_row = p.resid + (long long)(row_ok ? row : 0) * p.ldr;
+                prefetch(n0);
+            }
             mbar_wait<kCtaGroup == 2>(&tmem_full_bar[acc], acc_phase, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
 
-            if constexpr (kEpi == EPI_STORE || kEpi == EPI_GATED_RES) {
-                const __nv_bfloat16* gate_row = nullptr;
-                if constexpr (kEpi == EPI_GATED_RES)
-                    gate_row = p.gate + (long long)((row_ok ? row : 0) / p.rows_per_sample) * p.ld_gate;
+            if constexpr (kEpi == EPI_GATED_RES) {
+                // x' = x + bf16(bf16(acc + bias) * gate); operands prefetched above / one chunk ahead
+#pragma unroll 1
+                for (int c = 0; c < bn_eff / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_x32(taddr + c * 32, r);
+                    uint32_t res_p[16], gate_p[16], bias_p[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        res_p[4 * j] = res_n[j].x; res_p[4 * j + 1] = res_n[j].y; res_p[4 * j + 2] = res_n[j].z; res_p[4 * j + 3] = res_n[j].w;
+                        gate_p[4 * j] = gate_n[j].x; gate_p[4 * j + 1] = gate_n[j].y; gate_p[4 * j + 2] = gate_n[j].z; gate_p[4 * j + 3] = gate_n[j].w;
+                        bias_p[4 * j] = bias_n[j].x; bias_p[4 * j + 1] = bias_n[j].y; bias_p[4 * j + 2] = bias_n[j].z; bias_p[4 * j + 3] = bias_n[j].w;
+                    }
+                    const int col = n0 + c * 32;
+                    if (c + 1 < bn_eff / 32) prefetch(col + 32);
+                    tmem_ld_wait();
+                    uint32_t outp[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        // reference rounding points: y = bf16(acc+b); yg = bf16(y*gate); x' = bf16(x+yg)
+                        float a = bf16_round(__uint_as_float(r[2 * j]) + bf16_lo(bias_p[j]));
+                        float b = bf16_round(__uint_as_float(r[2 * j + 1]) + bf16_hi(bias_p[j]));
+                        a = bf16_round(a * bf16_lo(gate_p[j]));
+                        b = bf16_round(b * bf16_hi(gate_p[j]));
+                        outp[j] = pack_bf16x2(bf16_lo(res_p[j]) + a, bf16_hi(res_p[j]) + b);
+                    }
+                    if (row_ok) {
+                        uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            cp[j] = make_uint4(outp[4 * j], outp[4 * j + 1], outp[4 * j + 2], outp[4 * j + 3]);
+                    }
+                }
+            } else if constexpr (kEpi == EPI_STORE) {
 #pragma unroll 1
                 for (int c = 0; c < bn_eff / 32; ++c) {
                     uint32_t r[32];
@@ -261,39 +311,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 16; ++j) bias_p[j] = 0;
                     }
-                    if constexpr (kEpi == EPI_STORE) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float a = bf16_round(__uint_as_float(r[2 * j]) + bf16_lo(bias_p[j]));
-                            float b = bf16_round(__uint_as_float(r[2 * j + 1]) + bf16_hi(bias_p[j]));
-                            if (p.act == 1) { a = silu_f(a); b = silu_f(b); }
-                            outp[j] = pack_bf16x2(a, b);
-                        }
-                    } else {
-                        uint32_t res_p[16], gate_p[16];
-                        if (row_ok) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (long long)row * p.ldr + col);
-                            const uint4* gp = reinterpret_cast<const uint4*>(gate_row + col);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint4 v = __ldcg(rp + j);   // residual stream: rewritten every GEMM, keep it out of L1
-                                res_p[4 * j] = v.x; res_p[4 * j + 1] = v.y; res_p[4 * j + 2] = v.z; res_p[4 * j + 3] = v.w;
-                                uint4 g = __ldg(gp + j);
-                                gate_p[4 * j] = g.x; gate_p[4 * j + 1] = g.y; gate_p[4 * j + 2] = g.z; gate_p[4 * j + 3] = g.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) { res_p[j] = 0; gate_p[j] = 0; }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            // reference rounding points: y = bf16(acc+b); yg = bf16(y*gate); x' = bf16(x+yg)
-                            float a = bf16_round(__uint_as_float(r[2 * j]) + bf16_lo(bias_p[j]));
-                            float b = bf16_round(__uint_as_float(r[2 * j + 1]) + bf16_hi(bias_p[j]));
-                            a = bf16_round(a * bf16_lo(gate_p[j]));
-                            b = bf16_round(b * bf16_hi(gate_p[j]));
-                            outp[j] = pack_bf16x2(bf16_lo(res_p[j]) + a, bf16_hi(res_p[j]) + b);
-                        }
+                    for (int j = 0; j < 16; ++j) {
+                        float a = bf16_round(__uint_as_float(r[2 * j]) + bf16_lo(bias_p[j]));
+                        float b = bf16_round(__uint_as_float(r[2 * j + 1]) + bf16_hi(bias_p[j]));
+                        if (p.act == 1) { a = silu_f(a); b = silu_f(b); }
+                        outp[j] = pack_bf16x2(a, b);
                     }
                     if (row_ok) {
                         uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + col);
