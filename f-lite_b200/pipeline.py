@@ -83,9 +83,13 @@ def denoise_step(dit_model, latents, acc, context_input, mask_input, t_tensor, d
 @torch.no_grad()
 def denoise(dit_model, latents, negative_embeds, prompt_embeds, mask=None, num_inference_steps: int = 30,
             guidance_scale: float = 6.0, alpha: Optional[float] = None, acc_dtype=torch.bfloat16,
-            apg_config: Optional[APGConfig] = None, trace: Optional[list] = None, cfg_group=None):
+            apg_config: Optional[APGConfig] = None, trace: Optional[list] = None, cfg_group=None,
+            cuda_graph: bool = False):
     """The sampling loop of f_lite/pipeline.py:244-297 (acc_dtype=bf16) / f_lite/train.py:573-599
-    (acc_dtype=fp32).  ``mask`` covers ``[negative, positive]`` rows (None = all ones)."""
+    (acc_dtype=fp32).  ``mask`` covers ``[negative, positive]`` rows (None = all ones).
+
+    ``cuda_graph``: capture the DiT forward once and replay it every step (``graphs.GraphedForward``) -- for
+    launch-bound shapes; bit-identical to the eager loop.  Single-GPU only."""
     b = latents.shape[0]
     latents = latents.to(torch.bfloat16).contiguous().clone()
     acc = latents.to(acc_dtype).clone()
@@ -109,9 +113,23 @@ def denoise(dit_model, latents, negative_embeds, prompt_embeds, mask=None, num_i
     rows = 2 * b if (do_cfg and not split_cfg) else b
     # torch.tensor([t] * batch, dtype=model dtype) of pipeline.py:260, for every step, in one H2D copy
     t_all = torch.tensor([[t] * rows for t, _ in sched], dtype=latents.dtype).to(latents.device)
+    graphed = None
+    if cuda_graph:
+        if cfg_group is not None:
+            raise ValueError("cuda_graph=True is single-GPU only")
+        from .graphs import GraphedForward
+        graphed = GraphedForward(dit_model, latents, context_input, mask_input, t_all[0], duplicate_latents=do_cfg)
     for step, (t, dt) in enumerate(sched):
         t_tensor = t_all[step]
-        if apg and do_cfg and not split_cfg:
+        if graphed is not None:
+            out = graphed(t_tensor)
+            if apg and do_cfg:
+                ops.apg_euler(acc, out[:b], out[b:], guidance_scale, dt, apg_config.orthogonal_threshold, latents)
+            elif do_cfg:
+                ops.cfg_euler(acc, out[:b], out[b:], guidance_scale, dt, latents, do_cfg=True)
+            else:
+                ops.cfg_euler(acc, None, out, guidance_scale, dt, latents, do_cfg=False)
+        elif apg and do_cfg and not split_cfg:
             # Augmented Parallel Guidance (pipeline.py:276-287): the three global reductions and the update run on the
             # device (flite_apg_euler), no host sync.
             out = dit_model(torch.cat([latents] * 2), context_input, mask_input, t_tensor)
@@ -225,6 +243,7 @@ class FLitePipeline:
         negative_mask = kwargs.pop("negative_attention_mask", None)
         output_type = kwargs.pop("output_type", "pil")
         acc_dtype = kwargs.pop("acc_dtype", dtype)
+        cuda_graph = kwargs.pop("cuda_graph", False)       # replay the DiT forward from a CUDA graph (launch-bound shapes)
         if prompt_embeds is None:
             prompt_embeds, negative_embeds, prompt_mask, negative_mask = self.encode_prompt(
                 prompt, negative_prompt, device=device, dtype=dtype, return_index=self.return_index)
@@ -259,7 +278,7 @@ class FLitePipeline:
 
         self.dit_model.eval()
         latents = denoise(self.dit_model, latents, negative_embeds, prompt_embeds, mask, num_inference_steps,
-                          guidance_scale, alpha, acc_dtype=acc_dtype, apg_config=apg_config)
+                          guidance_scale, alpha, acc_dtype=acc_dtype, apg_config=apg_config, cuda_graph=cuda_graph)
         if output_type == "latent" or self.vae is None:
             return FLitePipelineOutput(images=latents)
 

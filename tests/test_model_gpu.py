@@ -370,3 +370,37 @@ def test_no_uninitialised_reads_with_poisoned_workspaces(hoist):
     again = flite_b200.denoise(m, lat0, neg, pos, mask, 3, 6.0)
     assert torch.isfinite(again.float()).all()
     assert torch.equal(again, clean)
+
+
+@pytest.mark.parametrize("mode", ["cfg", "apg", "nocfg", "fp32acc"])
+def test_cuda_graph_replay_is_bit_identical(mode, golden_dir):
+    """denoise(cuda_graph=True): the DiT forward captured once and replayed every step (graphs.GraphedForward) gives
+    exactly the eager loop's bits -- tiny model (the launch-bound case it exists for), 4 steps."""
+    import flite_b200
+    from oracle.make_golden import build_case
+    g = torch.load(os.path.join(golden_dir, "tiny_256_sampler.pt"), weights_only=False)
+    rec = g["recipe"]
+    sd, x, ctx, mask, _ = build_case(rec, device=DEV)
+    b = rec["batch"]
+    m = _model(rec["cfg"], sd)
+    kw = dict(num_inference_steps=4, guidance_scale=0.5 if mode == "nocfg" else 6.0,
+              apg_config=flite_b200.APGConfig(True, 0.03) if mode == "apg" else None,
+              acc_dtype=torch.float32 if mode == "fp32acc" else torch.bfloat16)
+    args = (m, x[:b].bfloat16(), ctx[:b].bfloat16(), ctx[b:].bfloat16(), mask)
+    eager = flite_b200.denoise(*args, **kw)
+    graphed = flite_b200.denoise(*args, cuda_graph=True, **kw)
+    assert torch.isfinite(eager.float()).all() and torch.equal(eager, graphed)
+
+
+def test_cuda_graph_replay_wide_model_without_context_hoisting():
+    import flite_b200
+    from oracle import synth
+    cfg = dict(synth.ARCH_10B, depth=2)
+    sd = synth.make_state_dict(cfg, 0, device=DEV)
+    m = _model(cfg, sd)
+    m.hoist_context = False                      # the context path is then captured inside the graph as well
+    x, ctx, mask = synth.make_inputs(cfg, 1, 1024, 1024, 256, valid_len=[200], device=DEV)
+    args = (m, x.bfloat16(), ctx[:1].bfloat16(), ctx[1:].bfloat16(), mask)
+    eager = flite_b200.denoise(*args, num_inference_steps=3)
+    graphed = flite_b200.denoise(*args, num_inference_steps=3, cuda_graph=True)
+    assert torch.equal(eager, graphed)
