@@ -42,10 +42,6 @@ constexpr int ATT_XCH = ATT_BAR + 128;          // float [2 parity][2 half][128 
 constexpr int ATT_SMEM_USED = ATT_XCH + 2048;
 constexpr int ATT_SMEM = 232448;                // 227 KB: everything the SM gives one CTA
 
-FLITE_DEVICE void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 FLITE_DEVICE float fast_exp2(float x) {
     float y;
     asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -26,6 +26,10 @@ __device__ unsigned int g_flite_abort = 0;   // 0 = ok, else (tag << 16 | blockI
 FLITE_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 FLITE_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+FLITE_DEVICE void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 FLITE_DEVICE uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

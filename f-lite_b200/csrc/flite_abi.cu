@@ -149,7 +149,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     static bool configured = false;
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kEpi == EPI_QKV_ROPE ? S::TOTAL_STAGED : S::TOTAL));
+                                      kEpi == EPI_QKV_ROPE ? S::TOTAL_QKV : S::TOTAL));
         configured = true;
     }
     const int tile_m = 128 * kCtaGroup;
@@ -189,8 +189,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     if (clusters > p.num_units) clusters = p.num_units;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * kCtaGroup);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = (kEpi == EPI_QKV_ROPE && p.stage_stores) ? S::TOTAL_STAGED : S::TOTAL;
+    cfg.blockDim = dim3(gemm_threads(kEpi));
+    cfg.dynamicSmemBytes = (kEpi == EPI_QKV_ROPE) ? S::TOTAL_QKV : S::TOTAL;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;

@@ -62,7 +62,10 @@ struct GemmParams {
 };
 
 constexpr int GEMM_BLOCK_K = 64;
-constexpr int GEMM_THREADS = 192;
+// warps: 0 TMA producer, 1 MMA issuer, 2.. epilogue.  The QKV epilogue (RoPE + QK-norm over a whole 256-column head per
+// row) is the heaviest one: it runs on TWO warpgroups, each owning one half of the (j, j+128) column pairs of every row.
+__host__ __device__ constexpr int gemm_epi_warpgroups(int epi) { return epi == 3 ? 2 : 1; }
+__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 128 * gemm_epi_warpgroups(epi); }
 
 template <int kCtaGroup, int BLOCK_N, int kStages>
 struct GemmSmem {
@@ -73,12 +76,16 @@ struct GemmSmem {
     static constexpr int BAR_OFFSET = kStages * STAGE_BYTES;
     static constexpr int STAGING_OFFSET = BAR_OFFSET + 256;           // 4 epilogue warps x 32 rows x 256 B
     static constexpr int STAGING_BYTES = 4 * 32 * 256;
+    static constexpr int XCH_OFFSET = STAGING_OFFSET + STAGING_BYTES;  // EPI_QKV_ROPE: [tile parity][column half][128 rows] fp32
+    static constexpr int XCH_BYTES = 2 * 2 * 128 * 4;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
-    static constexpr int TOTAL_STAGED = TOTAL + STAGING_BYTES;
+    // QKV epilogue: + staging + sum-of-squares exchange; 227 KB leaves 768 B of alignment slack (checked at run time)
+    static constexpr int QKV_USED = XCH_OFFSET + XCH_BYTES;
+    static constexpr int TOTAL_QKV = (QKV_USED + 1024 <= 232448) ? QKV_USED + 1024 : 232448;
 };
 
 template <int kCtaGroup, int BLOCK_N, int kStages, int kEpi>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(kEpi), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_b_half, const GemmParams p) {
     using S = GemmSmem<kCtaGroup, BLOCK_N, kStages>;
@@ -99,6 +106,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int warp_idx = threadIdx.x >> 5;
     const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0;
     const bool is_leader = cta_rank == 0;
+    if constexpr (kEpi == EPI_QKV_ROPE) {
+        // the QKV layout leaves < 1 KB of alignment slack: refuse to run (same answer in both CTAs, before any barrier)
+        if ((smem - smem_raw) + S::QKV_USED > S::TOTAL_QKV) {
+            if (threadIdx.x == 0) atomicCAS(&g_flite_abort, 0u, (97u << 16) | 0x80000000u);
+            return;
+        }
+    }
 
     if (warp_idx == 0 && elect_one()) {
         tma_prefetch_desc(&tmap_a);
@@ -112,7 +126,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&tmem_full_bar[i], 1);
-                mbar_init(&tmem_empty_bar[i], 4 * kCtaGroup);
+                mbar_init(&tmem_empty_bar[i], 4 * kCtaGroup * gemm_epi_warpgroups(kEpi));
             }
             fence_barrier_init();
         }
@@ -354,20 +368,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
             } else if constexpr (kEpi == EPI_QKV_ROPE) {
-                // One 256-column tile = one head of q, k or v; one thread = one token row of that head, so the
-                // RoPE pairs (j, j+128) and the RMS reduction over the head are thread-local.  The rotated bf16
-                // values of the whole head stay in registers (128 packed words); TMEM is released to the MMA warp
-                // as soon as it has been read, before the normalisation and the stores.
+                // One 256-column tile = one head of q, k or v; one ROW is handled by two threads (one per epilogue
+                // warpgroup, same TMEM lane): warpgroup h owns columns [64h, 64h+64) and their RoPE partners
+                // [128+64h, 128+64h+64), so the rotation pairs (j, j+128) stay thread-local and only the two partial sums
+                // of squares are exchanged through shared memory.  The rotated bf16 values stay in registers (64 packed
+                // words); TMEM is released to the MMA warp as soon as it has been read, before normalisation and stores.
                 static_assert(kEpi != EPI_QKV_ROPE || BLOCK_N == 256, "QKV epilogue needs one head per tile");
+                const int hw = (warp_idx - 2) >> 2;           // column half owned by this warpgroup
                 const bool do_norm = n0 < p.qk_cols;
                 const bool do_rope = do_norm && p.rope_cos != nullptr;
                 const int pos = (row_ok ? row : 0) % p.rows_per_sample;
                 const uint4* cosr = reinterpret_cast<const uint4*>(p.rope_cos + (long long)pos * 128);
                 const uint4* sinr = reinterpret_cast<const uint4*>(p.rope_sin + (long long)pos * 128);
-                uint32_t keep[128];   // [0,64): columns 0..127, [64,128): columns 128..255 (bf16 pairs)
+                uint32_t keep[64];   // [0,32): columns 64h..64h+63, [32,64): columns 128+64h.. (bf16 pairs)
                 float ssq = 0.f;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int c = hw * 8 + cc;
                     uint32_t x1[8], x2[8];
                     tmem_ld_x8(taddr + c * 8, x1);
                     tmem_ld_x8(taddr + 128 + c * 8, x2);
@@ -398,8 +415,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             a0 = y10; e0 = y20; a1 = y11; e1 = y21;
                         }
                         ssq += a0 * a0 + a1 * a1 + e0 * e0 + e1 * e1;
-                        keep[c * 4 + j] = pack_bf16x2(a0, a1);
-                        keep[64 + c * 4 + j] = pack_bf16x2(e0, e1);
+                        keep[cc * 4 + j] = pack_bf16x2(a0, a1);
+                        keep[32 + cc * 4 + j] = pack_bf16x2(e0, e1);
                     }
                 }
                 // all TMEM reads of this accumulator are done: hand it back to the MMA warp now
@@ -410,6 +427,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
                 }
                 __syncwarp();
+                // full-row sum of squares: exchange the two halves (double-buffered by tile parity; the two warps that
+                // share TMEM lane quarter q meet on named barrier 1 + q).  NOTE the summation order (own half + other
+                // half) differs between the two threads only by commutation, so both compute the same rstd bits.
+                {
+                    float* xch = reinterpret_cast<float*>(smem + S::XCH_OFFSET) + (it & 1) * 256;
+                    const int r_in_tile = q * 32 + lane;
+                    xch[hw * 128 + r_in_tile] = ssq;
+                    named_bar_sync(1 + q, 64);
+                    const float other = xch[(hw ^ 1) * 128 + r_in_tile];
+                    ssq = (hw == 0) ? ssq + other : other + ssq;
+                }
                 const float rstd = do_norm ? rsqrtf(ssq * (1.0f / 256.0f) + p.eps) : 1.0f;
                 long long out_off = (long long)row * p.ldc + n0;
                 __nv_bfloat16* out_base = p.C;
@@ -430,44 +458,48 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 if (p.stage_stores) {
                     // warp-local transpose through shared memory: lane = row on the way in, lane = 16-byte chunk of a
-                    // row on the way out (two rows of 256 B per store instruction); chunks XOR-swizzled by the row
-                    uint8_t* stg = smem + S::STAGING_OFFSET + (warp_idx - 2) * (32 * 256);
+                    // row segment on the way out (four rows x 128 contiguous bytes per store instruction); chunks are
+                    // XOR-swizzled by the row.  Two passes: columns [64h, 64h+64), then [128+64h, 128+64h+64).
+                    uint8_t* stg = smem + S::STAGING_OFFSET + (warp_idx - 2) * (32 * 128);
                     const unsigned long long my_ptr = row_ok ? (unsigned long long)(out_base + out_off) : 0ull;
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
+                    for (int seg = 0; seg < 2; ++seg) {
 #pragma unroll
-                        for (int u = 0; u < 16; ++u) {
+                        for (int u = 0; u < 8; ++u) {
                             uint32_t o[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const uint32_t v = keep[hf * 64 + 4 * u + j];
+                                const uint32_t v = keep[seg * 32 + 4 * u + j];
                                 o[j] = do_norm ? pack_bf16x2(bf16_lo(v) * rstd, bf16_hi(v) * rstd) : v;
                             }
-                            *reinterpret_cast<uint4*>(stg + lane * 256 + ((u ^ (lane & 15)) << 4)) =
+                            *reinterpret_cast<uint4*>(stg + lane * 128 + ((u ^ (lane & 7)) << 4)) =
                                 make_uint4(o[0], o[1], o[2], o[3]);
                         }
                         __syncwarp();
-                        const int c = lane & 15;
+                        const int c = lane & 7;
 #pragma unroll 4
-                        for (int i2 = 0; i2 < 16; ++i2) {
-                            const int r = 2 * i2 + (lane >> 4);
-                            const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 256 + ((c ^ (r & 15)) << 4));
+                        for (int i2 = 0; i2 < 8; ++i2) {
+                            const int r = 4 * i2 + (lane >> 3);
+                            const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
                             const unsigned long long rp = __shfl_sync(0xffffffffu, my_ptr, r);
-                            if (rp != 0ull) reinterpret_cast<uint4*>(rp)[hf * 16 + c] = v;
+                            if (rp != 0ull) reinterpret_cast<uint4*>(rp)[seg * 16 + hw * 8 + c] = v;
                         }
                         __syncwarp();
                     }
                 } else if (row_ok) {
                     uint4* cp = reinterpret_cast<uint4*>(out_base + out_off);
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) {
-                        uint32_t o[4];
+                    for (int seg = 0; seg < 2; ++seg) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t v = keep[4 * u + j];
-                            o[j] = do_norm ? pack_bf16x2(bf16_lo(v) * rstd, bf16_hi(v) * rstd) : v;
+                        for (int u = 0; u < 8; ++u) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t v = keep[seg * 32 + 4 * u + j];
+                                o[j] = do_norm ? pack_bf16x2(bf16_lo(v) * rstd, bf16_hi(v) * rstd) : v;
+                            }
+                            cp[seg * 16 + hw * 8 + u] = make_uint4(o[0], o[1], o[2], o[3]);
                         }
-                        cp[u] = make_uint4(o[0], o[1], o[2], o[3]);
                     }
                 }
                 continue;   // barrier already signalled
