@@ -90,6 +90,36 @@ def decode_to_image(dec: Decoder, latents: torch.Tensor, gain: float = 1.0) -> t
     return (x / 2 + 0.5).clamp(0, 1)
 
 
+def map_diffusers_names(sd):
+    """State dict with diffusers' AutoencoderKL decoder names (as used by flite_b200.vae) -> this file's names."""
+    out = {}
+    up_idx = 0
+    for k, v in sd.items():
+        k = k[len("decoder."):]
+        if k.startswith("mid_block.resnets.0."):
+            out["mid.0." + k[len("mid_block.resnets.0."):]] = v
+        elif k.startswith("mid_block.resnets.1."):
+            out["mid.2." + k[len("mid_block.resnets.1."):]] = v
+        elif k.startswith("mid_block.attentions.0."):
+            r = k[len("mid_block.attentions.0."):]
+            r = (r.replace("group_norm.", "norm.").replace("to_q.", "q.").replace("to_k.", "k.").replace("to_v.", "v.")
+                  .replace("to_out.0.", "o."))
+            out["mid.1." + r] = v
+        elif k.startswith("up_blocks."):
+            _, i, kind, j, rest = k.split(".", 4)
+            i, j = int(i), int(j)
+            base = i * 5                       # 3 resnets + upsample + conv per block in the oracle's Sequential
+            if kind == "resnets":
+                out[f"up.{base + j}." + rest.replace("conv_shortcut.", "shortcut.")] = v
+            else:                              # upsamplers.0.conv.*
+                out[f"up.{base + 4}." + rest[len("conv."):]] = v
+        elif k.startswith("conv_norm_out."):
+            out["norm_out." + k[len("conv_norm_out."):]] = v
+        else:
+            out[k] = v
+    return out
+
+
 def toy_decode(z: torch.Tensor) -> torch.Tensor:
     """Deterministic, cheap stand-in for ``AutoencoderKL.decode`` used by the pipeline golden fixture
     (oracle/ref_pipeline_shim.py): 3 channel mixes of the latent, 8x nearest upsampling."""

@@ -1,6 +1,7 @@
 """GPU parity of the whole denoise path against the reference: golden vectors of the real module
 (tests/golden, generated in the build container), the oracle restatement run on the same device, and
 size-independent properties at the full 10B-architecture width."""
+import math
 import os
 
 import pytest
@@ -450,3 +451,30 @@ def test_all_masked_context_rows_give_zero_cross_attention():
     assert torch.isfinite(v.float()).all() and rel(v, v_or) <= TOL
     cb2 = cb.clone(); cb2[0] = 77.0               # fully masked rows are never read
     assert torch.equal(m(xb, cb2, mb, t), v)
+
+
+def test_product_vae_decoder_bf16_channels_last_vs_fp32_restatement():
+    """flite_b200.vae.AutoencoderKL (diffusers parameter names, bf16, channels_last, cuDNN) against the fp32 oracle
+    decoder with the same weights: decoded image PSNR, then the flite pipeline tail on top of it."""
+    from flite_b200 import ops, vae
+    from oracle import vae_decoder
+    torch.manual_seed(0)
+    m = vae.AutoencoderKL().to(DEV)
+    for p_ in m.parameters():
+        if p_.dim() > 1:
+            p_.data.uniform_(-1, 1).mul_((3.0 / p_.shape[1:].numel()) ** 0.5)
+    ref = vae_decoder.Decoder().to(DEV).eval()
+    ref.load_state_dict(vae_decoder.map_diffusers_names(m.state_dict()), strict=True)
+    mb = vae.AutoencoderKL().to(DEV)
+    mb.load_state_dict(m.state_dict())
+    mb = mb.to(torch.bfloat16).to(memory_format=torch.channels_last).eval()
+    lat = torch.randn(2, 16, 32, 32, device=DEV).bfloat16()
+    z = ops.latent_unscale(lat, mb.config.scaling_factor, mb.config.shift_factor)
+    img = ops.image_to_uint8(mb.decode(z).sample)                                  # [B, H, W, 3] uint8
+    with torch.no_grad():
+        x32 = ref(z.float())
+    ref_img = ((x32 / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1)
+    mse = ((img.float() - ref_img.float()) / 255).pow(2).mean().item()
+    psnr = 10 * math.log10(1.0 / max(mse, 1e-12))
+    print(f"bf16 product decoder vs fp32 restatement: PSNR {psnr:.1f} dB, image std {ref_img.float().std().item():.1f}")
+    assert img.shape == (2, 256, 256, 3) and ref_img.float().std().item() > 10 and psnr >= 30.0

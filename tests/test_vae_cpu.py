@@ -5,42 +5,12 @@ import torch
 from oracle import vae_decoder
 
 
-def _map_to_oracle(sd):
-    """flite_b200.vae (diffusers names) -> oracle/vae_decoder.py (Sequential indices)."""
-    out = {}
-    up_idx = 0
-    for k, v in sd.items():
-        k = k[len("decoder."):]
-        if k.startswith("mid_block.resnets.0."):
-            out["mid.0." + k[len("mid_block.resnets.0."):]] = v
-        elif k.startswith("mid_block.resnets.1."):
-            out["mid.2." + k[len("mid_block.resnets.1."):]] = v
-        elif k.startswith("mid_block.attentions.0."):
-            r = k[len("mid_block.attentions.0."):]
-            r = (r.replace("group_norm.", "norm.").replace("to_q.", "q.").replace("to_k.", "k.").replace("to_v.", "v.")
-                  .replace("to_out.0.", "o."))
-            out["mid.1." + r] = v
-        elif k.startswith("up_blocks."):
-            _, i, kind, j, rest = k.split(".", 4)
-            i, j = int(i), int(j)
-            base = i * 5                       # 3 resnets + upsample + conv per block in the oracle's Sequential
-            if kind == "resnets":
-                out[f"up.{base + j}." + rest.replace("conv_shortcut.", "shortcut.")] = v
-            else:                              # upsamplers.0.conv.*
-                out[f"up.{base + 4}." + rest[len("conv."):]] = v
-        elif k.startswith("conv_norm_out."):
-            out["norm_out." + k[len("conv_norm_out."):]] = v
-        else:
-            out[k] = v
-    return out
-
-
 def test_decoder_matches_oracle_restatement_fp32():
     from flite_b200 import vae
     torch.manual_seed(0)
     m = vae.AutoencoderKL().eval()
     ref = vae_decoder.Decoder().eval()
-    missing, unexpected = ref.load_state_dict(_map_to_oracle(m.state_dict()), strict=True)
+    missing, unexpected = ref.load_state_dict(vae_decoder.map_diffusers_names(m.state_dict()), strict=True)
     assert not missing and not unexpected
     z = torch.randn(2, 16, 8, 8)
     with torch.no_grad():
