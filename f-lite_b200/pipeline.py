@@ -84,7 +84,7 @@ def denoise_step(dit_model, latents, acc, context_input, mask_input, t_tensor, d
 def denoise(dit_model, latents, negative_embeds, prompt_embeds, mask=None, num_inference_steps: int = 30,
             guidance_scale: float = 6.0, alpha: Optional[float] = None, acc_dtype=torch.bfloat16,
             apg_config: Optional[APGConfig] = None, trace: Optional[list] = None, cfg_group=None,
-            cuda_graph: bool = False):
+            cuda_graph: bool = False, progress=None):
     """The sampling loop of f_lite/pipeline.py:244-297 (acc_dtype=bf16) / f_lite/train.py:573-599
     (acc_dtype=fp32).  ``mask`` covers ``[negative, positive]`` rows (None = all ones).
 
@@ -119,7 +119,9 @@ def denoise(dit_model, latents, negative_embeds, prompt_embeds, mask=None, num_i
             raise ValueError("cuda_graph=True is single-GPU only")
         from .graphs import GraphedForward
         graphed = GraphedForward(dit_model, latents, context_input, mask_input, t_all[0], duplicate_latents=do_cfg)
-    for step, (t, dt) in enumerate(sched):
+    steps_iter = range(len(sched)) if progress is None else progress(range(len(sched)))   # pipeline.py:250 progress_bar
+    for step in steps_iter:
+        t, dt = sched[step]
         t_tensor = t_all[step]
         if graphed is not None:
             out = graphed(t_tensor)
@@ -145,6 +147,10 @@ def denoise(dit_model, latents, negative_embeds, prompt_embeds, mask=None, num_i
                                cfg_group=cfg_group if split_cfg else None)
         if trace is not None:
             trace.append(out.clone())
+    # one synchronisation per trajectory: surface a kernel-side barrier time-out (flite_watchdog_status) instead of
+    # returning whatever the aborted kernels left behind
+    from . import _lib
+    _lib.watchdog_ok()
     return latents if acc_dtype == torch.bfloat16 else acc
 
 
@@ -172,8 +178,27 @@ class FLitePipeline:
                 m.to(device=torch_device, dtype=torch_dtype)
         return self
 
-    def progress_bar(self, it):
-        return it
+    # pipeline.py:84-102: memory / progress helpers of the reference surface
+    def enable_vae_slicing(self):
+        if hasattr(self.vae, "enable_slicing"):
+            self.vae.enable_slicing()
+
+    def enable_vae_tiling(self):
+        if hasattr(self.vae, "enable_tiling"):
+            self.vae.enable_tiling()
+
+    def set_progress_bar_config(self, **kwargs):
+        self._progress_bar_config = kwargs
+
+    def progress_bar(self, iterable=None, **kwargs):
+        config = {**(getattr(self, "_progress_bar_config", None) or {}), **kwargs}
+        if config.get("disable", False):
+            return iterable
+        try:
+            from tqdm.auto import tqdm
+        except ImportError:
+            return iterable
+        return tqdm(iterable, **config)
 
     # the system turn the reference puts in front of every caption (f_lite/pipeline.py:105); F Lite was trained with it,
     # so it is part of the text-conditioning interface, not a tunable
@@ -278,7 +303,8 @@ class FLitePipeline:
 
         self.dit_model.eval()
         latents = denoise(self.dit_model, latents, negative_embeds, prompt_embeds, mask, num_inference_steps,
-                          guidance_scale, alpha, acc_dtype=acc_dtype, apg_config=apg_config, cuda_graph=cuda_graph)
+                          guidance_scale, alpha, acc_dtype=acc_dtype, apg_config=apg_config, cuda_graph=cuda_graph,
+                          progress=self.progress_bar)
         if output_type == "latent" or self.vae is None:
             return FLitePipelineOutput(images=latents)
 

@@ -136,3 +136,29 @@ def test_pipeline_signature_matches_reference():
             p["guidance_scale"].default) == (1024, 1024, 30, 6.0)
     fsig = inspect.signature(flite_b200.DiT.forward)
     assert list(fsig.parameters)[:5] == ["self", "x", "context", "context_attn_mask", "timesteps"]  # model.py:526
+
+
+def test_pipeline_public_surface_matches_reference():
+    """Attributes / helper methods of f_lite.pipeline.FLitePipeline that user code touches (pipeline.py:47-102,176-184;
+    generate.py:77-78 calls pipe.vae.enable_slicing / enable_tiling through these)."""
+    P = pipeline.FLitePipeline
+    for name in ("enable_vae_slicing", "enable_vae_tiling", "set_progress_bar_config", "progress_bar", "encode_prompt",
+                 "to", "_convert_caption_to_messages"):
+        assert callable(getattr(P, name)), name
+    assert P.model_cpu_offload_seq == "text_encoder->dit_model->vae"
+
+    class V:
+        sliced = tiled = False
+
+        def enable_slicing(self): self.sliced = True
+        def enable_tiling(self): self.tiled = True
+
+    pipe = P(torch.nn.Linear(1, 1), V(), None, None)
+    pipe.enable_vae_slicing(); pipe.enable_vae_tiling()
+    assert pipe.vae.sliced and pipe.vae.tiled and pipe.vae_scale_factor == 8 and pipe.return_index == -8
+    pipe.set_progress_bar_config(disable=True)
+    assert list(pipe.progress_bar(range(3))) == [0, 1, 2]
+    o = pipeline.FLitePipelineOutput(images=[1])
+    assert o.images == [1]
+    a = pipeline.APGConfig()
+    assert a.enabled is True and a.orthogonal_threshold == 0.03          # pipeline.py:25-31

@@ -37,6 +37,7 @@ for p in vae.parameters():
     if p.dim() > 1: p.data.copy_((torch.rand(p.shape, device=dev, generator=g) * 2 - 1) * (3.0 / p.shape[1:].numel()) ** 0.5)
 vae = vae.to(memory_format=torch.channels_last).eval()
 pipe = flite_b200.FLitePipeline(model, vae, None, None)
+pipe.set_progress_bar_config(disable=True)
 b = args.images_per_gpu
 emb = torch.randn((b, 256, cfg["cross_attn_input_size"]), device=dev, generator=g).bfloat16()
 call = lambda steps, seed: pipe(prompt=None, height=args.res, width=args.res, num_inference_steps=steps, guidance_scale=6.0,
