@@ -3,7 +3,7 @@ library baselines (cuBLAS bf16 on the hot GEMM shapes, FA2 / SDPA at head_dim 25
 the parity tests proper live in tests/."""
 import json, os, sys, time, traceback
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import flite_b200
 from flite_b200 import ops, _lib
 

@@ -2,7 +2,7 @@
 restatement of the reference run on the same GPU in bf16 ("the reference bf16 path") and in fp32."""
 import json, os, sys, time
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import flite_b200
 from flite_b200 import _lib
 from oracle import dit_oracle, synth

@@ -2,7 +2,7 @@
 New path trajectory vs the reference bf16 trajectory (oracle on the same GPU), both decoded by the same decoder."""
 import json, os, sys, time
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import flite_b200
 from oracle import dit_oracle, sampler_oracle, synth, vae_decoder
 dev = "cuda"

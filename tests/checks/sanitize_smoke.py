@@ -2,7 +2,7 @@
 decode tail, plus the peer-memory kernels in single-GPU loopback."""
 import os, sys, ctypes
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import flite_b200
 from flite_b200 import ops, _lib
 from oracle import synth, vae_decoder
