@@ -182,6 +182,31 @@ FLITE_DEVICE void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* desc, uint6
         : "memory");
 }
 
+// Same loads with an L2 eviction-priority hint (createpolicy encodings as used by CUTLASS' TMA::CacheHintSm90):
+// evict_first for an operand that streams past once, evict_last for the operand the rasterisation wants resident.
+constexpr unsigned long long L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr unsigned long long L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr unsigned long long L2_EVICT_LAST = 0x14F0000000000000ull;
+
+FLITE_DEVICE void tma_load_2d_hint(void* smem_dst, const CUtensorMap* desc, uint64_t* bar, int c0, int c1,
+                                   unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+        "[%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+FLITE_DEVICE void tma_load_2d_cg2_hint(void* smem_dst, const CUtensorMap* desc, uint64_t* bar, uint32_t bar_rank,
+                                       int c0, int c1, unsigned long long policy) {
+    uint32_t bar_addr = mapa_shared(smem_u32(bar), bar_rank);
+    uint32_t dst_addr = mapa_shared(smem_u32(smem_dst), cluster_ctarank());
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], "
+        "[%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst_addr), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_addr), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+
 FLITE_DEVICE void tma_store_2d(const CUtensorMap* desc, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)

@@ -184,6 +184,12 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         }
         if (g > num_m_tiles) g = num_m_tiles;
         p.band_m = (int)g;
+        // L2 hints (FLITE_TUNE_GEMM_HINT_A / _B: 0 auto, 1 none, 2 evict_first, 3 evict_last)
+        auto policy = [](int v) -> unsigned long long {
+            return v == 2 ? L2_EVICT_FIRST : v == 3 ? L2_EVICT_LAST : 0ull;
+        };
+        p.hint_a = policy(g_tuning[FLITE_TUNE_GEMM_HINT_A]);
+        p.hint_b = policy(g_tuning[FLITE_TUNE_GEMM_HINT_B]);
     }
     int clusters = max_clusters;
     if (clusters > p.num_units) clusters = p.num_units;

@@ -59,6 +59,9 @@ struct GemmParams {
     // Rasterisation: tiles are ordered band by band (band_m consecutive M-tiles), N-tile by N-tile inside a band and
     // M fastest, so that a band of A (band_m x TILE_M x K) stays L2-resident while W streams past it once per band.
     int band_m;
+    // L2 eviction-priority hints of the A / W tile loads (0 = plain load); chosen with the band height so that the operand
+    // the rasterisation keeps resident is evict_last and the one that streams past it is evict_first.
+    unsigned long long hint_a, hint_b;
 };
 
 constexpr int GEMM_BLOCK_K = 64;
@@ -183,12 +186,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     uint8_t* sb = sa + S::A_BYTES;
                     if constexpr (kCtaGroup == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
-                        tma_load_2d(sb, tb, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+                        if (p.hint_a) tma_load_2d_hint(sa, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0, p.hint_a);
+                        else tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+                        if (p.hint_b) tma_load_2d_hint(sb, tb, &full_bar[stage], kb * GEMM_BLOCK_K, n0, p.hint_b);
+                        else tma_load_2d(sb, tb, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
                     } else {
                         if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
-                        tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], 0, kb * GEMM_BLOCK_K, m0);
-                        tma_load_2d_cg2(sb, tb, &full_bar[stage], 0, kb * GEMM_BLOCK_K, n0);
+                        if (p.hint_a) tma_load_2d_cg2_hint(sa, &tmap_a, &full_bar[stage], 0, kb * GEMM_BLOCK_K, m0, p.hint_a);
+                        else tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], 0, kb * GEMM_BLOCK_K, m0);
+                        if (p.hint_b) tma_load_2d_cg2_hint(sb, tb, &full_bar[stage], 0, kb * GEMM_BLOCK_K, n0, p.hint_b);
+                        else tma_load_2d_cg2(sb, tb, &full_bar[stage], 0, kb * GEMM_BLOCK_K, n0);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }

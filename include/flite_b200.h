@@ -65,6 +65,8 @@ extern "C" {
 #define FLITE_TUNE_ATTN_STAGED_STORES 7 /* 1 = 2-CTA attention stores whole output rows via a shared-memory transpose (always on for peer stores) */
 #define FLITE_TUNE_PDL 8             /* 1 = GEMM / attention / rmsnorm kernels use programmatic dependent launch; default 0 = off:
                                         measured 1 % SLOWER at C2 (profiles/r1e_ab_pdl.json) -- the step is power-capped, idle gaps are free */
+#define FLITE_TUNE_GEMM_HINT_A 9      /* L2 eviction hint of the GEMM's A-tile TMA loads: 0 auto | 1 none | 2 evict_first | 3 evict_last */
+#define FLITE_TUNE_GEMM_HINT_B 10     /* same for the W-tile loads */
 #define FLITE_TUNE_GEMM_BAND 5       /* 0 = L2-aware band rasterisation for large M (default), 1 = single band */
 int flite_set_tuning(int key, int value);
 
