@@ -33,6 +33,8 @@ SIGNATURES = {
     "flite_rmsnorm_modulate": [_P, _L, _P, _L, _P, _I, _P, _P, _L, _I, _I, _I, _F, _P],
     "flite_rope_qknorm": [_P, _L, _I, _I, _P, _P, _I, _F, _P],
     "flite_patch_embed": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "flite_patch_gather": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "flite_get_tuning": [_I],
     "flite_permute_021": [_P, _P, _I, _I, _I, _P],
     "flite_timestep_embed": [_P, _I, _P, _P, _I, _I, _P],
     "flite_unpatchify": [_P, _L, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -431,6 +431,34 @@ __global__ void p2p_wait_kernel(const unsigned int* flags, int n, unsigned int v
 }
 
 // ------------------------------------------------------------------------------------------
+// Patchify as a tensor-core GEMM (f_lite/model.py:318-328,535): this kernel only builds the im2col rows
+//   A[b * n_img + i, k] = x[b, c, hy*P + p1, wx*P + p2],  k = (c, p1, p2)   (i-th IMAGE token of this rank's slice)
+// and copies the learned register-token rows into the token matrix; the projection itself (K = C*P*P) then runs on
+// gemm_bf16_kernel (+bias) straight into the image rows of the token matrix, one launch per sample.
+// One block per local token row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+patch_gather_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ reg_tokens,
+                    __nv_bfloat16* __restrict__ A, __nv_bfloat16* __restrict__ out, int B, int C, int H, int W, int P,
+                    int d, int n_reg, int tok_offset, int tok_count, int n_reg_local) {
+    const int r = blockIdx.x;                       // local row: (sample, local token)
+    const int b = r / tok_count, t = r - b * tok_count, l = tok_offset + t;
+    if (l < n_reg) {
+        const uint4* src = reinterpret_cast<const uint4*>(reg_tokens + (long long)l * d);
+        uint4* dst = reinterpret_cast<uint4*>(out + (long long)r * d);
+        for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+        return;
+    }
+    const int kdim = C * P * P, wp = W / P;
+    const int pi = l - n_reg, hy = pi / wp, wx = pi - hy * wp;
+    const long long arow = (long long)b * (tok_count - n_reg_local) + (t - n_reg_local);
+    for (int k = threadIdx.x; k < kdim; k += blockDim.x) {
+        const int c = k / (P * P), p1 = (k / P) % P, p2 = k % P;
+        A[arow * kdim + k] = x[(((long long)b * C + c) * H + hy * P + p1) * W + wx * P + p2];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Sampler: fused CFG combine + Euler update (f_lite/pipeline.py:290,296-297; f_lite/train.py:596,599).
 //   v   = bf16(u + bf16(g * bf16(c - u)))                     (tensor ops in the model dtype)
 //   acc = acc + dt * v      bf16 accumulate (pipeline)  |  fp32 accumulate (train.py sample_images)

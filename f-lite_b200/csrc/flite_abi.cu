@@ -234,6 +234,8 @@ int flite_set_tuning(int key, int value) {
     return 0;
 }
 
+int flite_get_tuning(int key) { return (key >= 0 && key < 16) ? g_tuning[key] : 0; }
+
 int flite_check_device(void) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -411,6 +413,23 @@ int flite_patch_embed(const void* x, const void* w, const void* bias, const void
     if (kdim == 64) args(patch_embed_kernel<64>);
     else if (kdim == 16) args(patch_embed_kernel<16>);
     else return fail(FLITE_ERR_INVALID, "patch_embed: C*P*P = %d unsupported (16 or 64)", kdim);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int flite_patch_gather(const void* x, const void* reg_tokens, void* A, void* out, int B, int C, int H, int W, int P,
+                       int d, int n_reg, int tok_offset, int tok_count, void* stream) {
+    if (!x || !A || !out || (n_reg > 0 && !reg_tokens)) return fail(FLITE_ERR_INVALID, "patch_gather: null pointer");
+    if (P <= 0 || H % P || W % P || d % 8) return fail(FLITE_ERR_INVALID, "patch_gather: H, W must be multiples of the patch size, d of 8");
+    const int L_full = n_reg + (H / P) * (W / P);
+    if (tok_count <= 0) { tok_offset = 0; tok_count = L_full; }
+    if (tok_offset < 0 || tok_offset + tok_count > L_full) return fail(FLITE_ERR_INVALID, "patch_gather: token slice out of range");
+    if (B <= 0) return 0;
+    int n_reg_local = (n_reg < tok_offset + tok_count ? n_reg : tok_offset + tok_count) - tok_offset;
+    if (n_reg_local < 0) n_reg_local = 0;
+    patch_gather_kernel<<<B * tok_count, 128, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)reg_tokens, (__nv_bfloat16*)A, (__nv_bfloat16*)out, B, C, H, W, P,
+        d, n_reg, tok_offset, tok_count, n_reg_local);
     LAUNCH_CHECK();
     return 0;
 }

@@ -39,6 +39,7 @@ def _traced(label_fn):
             tr.append((label_fn(*args, **kwargs), e0, e1))
             return r
         wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+        wrapper.__wrapped__ = fn
         return wrapper
     return deco
 
@@ -184,9 +185,16 @@ def rope_qknorm_(buf: torch.Tensor, n_slots: int, cos: Optional[torch.Tensor], s
     LAUNCHES[0] += 1
 
 
+_PATCH_WS = {}
+
+
 @_traced(lambda x, *a, **k: f"patch_embed {tuple(x.shape)}")
 def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, reg_tokens: torch.Tensor, patch: int,
                 out: Optional[torch.Tensor] = None, tok_offset: int = 0, tok_count: int = 0) -> torch.Tensor:
+    """Conv2d(k = s = patch) + register tokens (model.py:324-328,535) -> token rows [B * tok_count, d].
+
+    C*P*P % 64 == 0 (F Lite: 16 * 2 * 2): an im2col gather (flite_patch_gather) followed by the tcgen05 GEMM (+bias)
+    straight into the image rows of every sample; otherwise the CUDA-core patch_embed kernel."""
     lib = _lib.load()
     for t, n in ((x, "x"), (weight, "weight"), (bias, "bias"), (reg_tokens, "register_tokens")):
         _chk(t, n)
@@ -195,9 +203,30 @@ def patch_embed(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, reg_t
     B, C, H, W = x.shape
     d = weight.shape[0]
     n_reg = reg_tokens.shape[-2]
-    rows = B * (tok_count if tok_count > 0 else n_reg + (H // patch) * (W // patch))
+    L_full = n_reg + (H // patch) * (W // patch)
+    if tok_count <= 0:
+        tok_offset, tok_count = 0, L_full
+    rows = B * tok_count
     if out is None:
         out = torch.empty((rows, d), dtype=BF16, device=x.device)
+    kdim = C * patch * patch
+    if kdim % 64 == 0 and lib.flite_get_tuning(11) == 0:
+        n_reg_local = max(0, min(n_reg, tok_offset + tok_count) - tok_offset)
+        n_img = tok_count - n_reg_local
+        key = (x.device, B * n_img, kdim)
+        A = _PATCH_WS.get(key)
+        if A is None:
+            A = torch.empty((max(B * n_img, 1), kdim), dtype=BF16, device=x.device)
+            _PATCH_WS[key] = A
+        _lib.check(lib.flite_patch_gather(x.data_ptr(), reg_tokens.data_ptr(), A.data_ptr(), out.data_ptr(), B, C, H, W,
+                                          patch, d, n_reg, tok_offset, tok_count, _stream()), "patch_gather")
+        LAUNCHES[0] += 1
+        if n_img > 0:
+            w2 = weight.view(d, kdim)
+            for b in range(B):
+                gemm.__wrapped__(A[b * n_img:(b + 1) * n_img], w2, bias,
+                                 out=out[b * tok_count + n_reg_local:(b + 1) * tok_count])
+        return out
     _lib.check(lib.flite_patch_embed(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), reg_tokens.data_ptr(),
                                      out.data_ptr(), B, C, H, W, patch, d, n_reg, tok_offset, tok_count, _stream()),
                "patch_embed")

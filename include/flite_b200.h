@@ -67,8 +67,10 @@ extern "C" {
                                         measured 1 % SLOWER at C2 (profiles/r1e_ab_pdl.json) -- the step is power-capped, idle gaps are free */
 #define FLITE_TUNE_GEMM_HINT_A 9      /* L2 eviction hint of the GEMM's A-tile TMA loads: 0 auto | 1 none | 2 evict_first | 3 evict_last */
 #define FLITE_TUNE_GEMM_HINT_B 10     /* same for the W-tile loads */
+#define FLITE_TUNE_PATCH_EMBED 11     /* 0 auto: patchify = gather + tcgen05 GEMM when C*P*P % 64 == 0 | 1 CUDA-core patch_embed kernel */
 #define FLITE_TUNE_GEMM_BAND 5       /* 0 = L2-aware band rasterisation for large M (default), 1 = single band */
 int flite_set_tuning(int key, int value);
+int flite_get_tuning(int key);   /* current value of a knob (0 for an unknown key) */
 
 int flite_abi_version(void);
 const char* flite_last_error(void);
@@ -121,6 +123,14 @@ int flite_rope_qknorm(void* buf, int64_t ld, int rows, int n_slots, const void* 
 int flite_patch_embed(const void* x, const void* w, const void* bias, const void* reg_tokens, void* out,
                       int B, int C, int H, int W, int P, int d, int n_reg, int tok_offset, int tok_count,
                       void* stream);
+
+/* Patchify on the tensor cores: builds the im2col matrix A [B * n_img, C*P*P] (k order (c, p1, p2), n_img = image tokens
+ * of the slice [tok_offset, tok_offset + tok_count)) and copies the register-token rows of the slice into `out`
+ * [B * tok_count, d]; the caller then runs flite_gemm_bf16(A_b, conv weight viewed as [d, C*P*P], +bias) into the image
+ * rows of every sample.  Replaces Conv2d k = s = P + cat(register_tokens) (model.py:324-328,535) like flite_patch_embed,
+ * which does the projection on CUDA cores and is kept for C*P*P not a multiple of 64. */
+int flite_patch_gather(const void* x, const void* reg_tokens, void* A, void* out, int B, int C, int H, int W, int P,
+                       int d, int n_reg, int tok_offset, int tok_count, void* stream);
 
 /* dst[n1, n0, n2] = src[n0, n1, n2] (bf16, n2 % 8 == 0): layout transform around the Ulysses all-to-alls. */
 int flite_permute_021(const void* src, void* dst, int n0, int n1, int n2, void* stream);

@@ -227,10 +227,18 @@ def test_patch_embed_and_unpatchify(B, H, W, d):
     C, P = 16, 2
     x = rnd(B, C, H, W, seed=1)
     w, b, reg = rnd(d, C, P, P, scale=0.1, seed=2), rnd(d, seed=3), rnd(1, 16, d, seed=4)
-    tok = ops.patch_embed(x, w, b, reg, P)
+    tok = ops.patch_embed(x, w, b, reg, P)                       # im2col gather + tcgen05 GEMM (C*P*P = 64)
     ref = F.conv2d(x.float(), w.float(), b.float(), stride=P).flatten(2).transpose(1, 2)   # model.py:324-328
     ref = torch.cat([reg.float().repeat(B, 1, 1), ref], 1).reshape(-1, d)
     assert rel(tok, ref) <= 3e-3
+    from flite_b200 import _lib
+    lib = _lib.load()
+    lib.flite_set_tuning(11, 1)                                  # the CUDA-core kernel gives the same tokens
+    try:
+        tok_old = ops.patch_embed(x, w, b, reg, P)
+    finally:
+        lib.flite_set_tuning(11, 0)
+    assert rel(tok_old, ref) <= 3e-3 and rel(tok, tok_old) <= 3e-3
     L = 16 + (H // P) * (W // P)
     assert torch.equal(tok.view(B, L, d)[:, :16], reg.repeat(B, 1, 1))
     tk = rnd(B * L, 64, seed=5)
