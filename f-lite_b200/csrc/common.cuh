@@ -26,6 +26,14 @@ __device__ unsigned int g_flite_abort = 0;   // 0 = ok, else (tag << 16 | blockI
 FLITE_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 FLITE_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// streaming 16-byte load: read-only path, do not keep the line in L1 (weights that are touched exactly once)
+FLITE_DEVICE uint4 ld_nc_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 FLITE_DEVICE void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

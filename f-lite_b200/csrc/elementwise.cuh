@@ -431,6 +431,81 @@ __global__ void p2p_wait_kernel(const unsigned int* flags, int n, unsigned int v
 }
 
 // ------------------------------------------------------------------------------------------
+// Skinny GEMM (M <= 8 rows) for the timestep path: time_embed MLP, adaLN_modulation, final_modulation
+// (f_lite/model.py:448-454,472,553-556,578) -- 358 MB of weights per step at the 10B architecture against a few KB of
+// activations: pure weight streaming, HBM-bound.  A 128-row tensor-core tile would leave most SMs idle (N / 128 CTAs,
+// each pulling its whole K extent alone), so: every W row is read exactly once with coalesced 16-byte streaming loads
+// spread over all SMs, the M activation rows come from L1, fp32 accumulation, warp + block reduction,
+// out[m, n] = act(bf16(acc + bias[n])) with the same rounding points as the EPI_STORE epilogue.
+// Algorithmic bytes per launch: N*K*2 (weights) + M*(K + N)*2.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int GEMV_ROWS(int maxm) { return 4; }   // 8 rows for M <= 2 measured slower (53 -> 67 us at 27648 x 3072)
+template <int MAXM>
+__global__ void __launch_bounds__(256)
+gemv_small_m_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_bfloat16* __restrict__ Wt, long long ldw,
+                    __nv_bfloat16* __restrict__ C, long long ldc, const __nv_bfloat16* __restrict__ bias, int act, int M,
+                    int N, int K) {
+    // A block owns GEMV_ROWS consecutive output columns (= rows of W) at a time; its 256 threads split the K extent, so
+    // every thread has GEMV_ROWS independent 16-byte weight loads in flight per step and the activation chunk it
+    // fetched from L1 is reused for all of them.
+    constexpr int ROWS = GEMV_ROWS(MAXM);
+    __shared__ float part[8][ROWS][MAXM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nchunk = K >> 3;                       // 16-byte chunks per row
+    for (int n0 = blockIdx.x * ROWS; n0 < N; n0 += gridDim.x * ROWS) {
+        float acc[ROWS][MAXM];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) acc[r][m] = 0.f;
+        for (int c = threadIdx.x; c < nchunk; c += 256) {
+            uint4 wv[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+                wv[r] = (n0 + r < N) ? ld_nc_stream(reinterpret_cast<const uint4*>(Wt + (long long)(n0 + r) * ldw) + c)
+                                     : make_uint4(0, 0, 0, 0);
+            float af[MAXM][8];
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) {
+                if (m < M) unpack8(__ldg(reinterpret_cast<const uint4*>(A + (long long)m * lda) + c), af[m]);
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                float wf[8];
+                unpack8(wv[r], wf);
+#pragma unroll
+                for (int m = 0; m < MAXM; ++m) {
+                    if (m < M) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[r][m] = fmaf(af[m][j], wf[j], acc[r][m]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) {
+                const float v = (m < M) ? warp_sum(acc[r][m]) : 0.f;
+                if (lane == 0) part[warp][r][m] = v;
+            }
+        __syncthreads();
+        if (threadIdx.x < ROWS * MAXM) {
+            const int r = threadIdx.x / MAXM, m = threadIdx.x % MAXM, n = n0 + r;
+            if (m < M && n < N) {
+                float v = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) v += part[w8][r][m];
+                v = bf16_round(v + (bias != nullptr ? __bfloat162float(bias[n]) : 0.f));
+                if (act == 1) v = silu_f(v);
+                C[(long long)m * ldc + n] = __float2bfloat16_rn(v);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Patchify as a tensor-core GEMM (f_lite/model.py:318-328,535): this kernel only builds the im2col rows
 //   A[b * n_img + i, k] = x[b, c, hy*P + p1, wx*P + p2],  k = (c, p1, p2)   (i-th IMAGE token of this rank's slice)
 // and copies the learned register-token rows into the token matrix; the projection itself (K = C*P*P) then runs on

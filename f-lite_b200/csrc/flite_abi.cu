@@ -507,6 +507,22 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
         return fail(FLITE_ERR_INVALID, "gemm: sequence-parallel head scatter needs the QKV epilogue and N = 3*256*ranks*heads_per_rank");
 
     if (variant == FLITE_GEMM_AUTO && g_tuning[FLITE_TUNE_GEMM_VARIANT]) variant = g_tuning[FLITE_TUNE_GEMM_VARIANT];
+    // skinny GEMM (timestep / modulation path): weight streaming on all SMs instead of N/128 tensor-core tiles
+    if ((variant == FLITE_GEMM_AUTO && M <= 8 && epilogue == EPI_STORE && K % 8 == 0) || variant == FLITE_GEMM_GEMV) {
+        if (M > 8 || epilogue != EPI_STORE)
+            return fail(FLITE_ERR_INVALID, "gemm: the GEMV variant handles M <= 8 with the plain epilogue");
+        const int rows = GEMV_ROWS(M <= 2 ? 2 : M <= 4 ? 4 : 8);
+        int blocks = (N + rows - 1) / rows;             // output columns per block iteration
+        const int cap = num_sms() * 8;
+        if (blocks > cap) blocks = (blocks + ((blocks + cap - 1) / cap) - 1) / ((blocks + cap - 1) / cap);   // equal shares
+        const __nv_bfloat16* a_ = (const __nv_bfloat16*)A; const __nv_bfloat16* w_ = (const __nv_bfloat16*)W;
+        __nv_bfloat16* c_ = (__nv_bfloat16*)C; const __nv_bfloat16* b_ = (const __nv_bfloat16*)bias;
+        if (M <= 2) gemv_small_m_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(a_, lda, w_, ldw, c_, ldc, b_, act, M, N, K);
+        else if (M <= 4) gemv_small_m_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(a_, lda, w_, ldw, c_, ldc, b_, act, M, N, K);
+        else gemv_small_m_kernel<8><<<blocks, 256, 0, (cudaStream_t)stream>>>(a_, lda, w_, ldw, c_, ldc, b_, act, M, N, K);
+        LAUNCH_CHECK();
+        return 0;
+    }
     if (variant == FLITE_GEMM_AUTO) {
         if (epilogue == EPI_QKV_ROPE) variant = (M > 128) ? FLITE_GEMM_2CTA_N256 : FLITE_GEMM_1CTA_N256;
         else if (N % 256 == 0 && M > 128) variant = FLITE_GEMM_2CTA_N256;

@@ -43,6 +43,7 @@ extern "C" {
 #define FLITE_GEMM_2CTA_N256 2
 #define FLITE_GEMM_1CTA_N128 3
 #define FLITE_GEMM_1CTA_N64 4
+#define FLITE_GEMM_GEMV 5        /* M <= 8, plain epilogue: one warp per output column, weight streaming (HBM-bound); AUTO picks it */
 
 /* attention kernel variants */
 #define FLITE_ATTN_AUTO 0

@@ -88,17 +88,19 @@ def test_rmsnorm_modulate(rows, d, B, mode):
 
 
 # ----------------------------------------------------------------------------- GEMM
-GEMM_SHAPES = [(128, 128, 64), (1, 128, 64), (2, 9216, 512), (200, 64, 512), (256, 512, 512), (333, 768, 192),
+GEMM_SHAPES = [(128, 128, 64), (1, 128, 64), (2, 9216, 512), (2, 27648, 3072), (8, 3072, 12288), (3, 192, 1024), (200, 64, 512), (256, 512, 512), (333, 768, 192),
                (2 * 272, 1536, 512), (2 * 4112, 3072, 3072), (16 * 1181, 768, 4096)]   # last: multi-band rasterisation
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_gemm_store_bias(M, N, K, variant):
     from flite_b200 import ops
     need = {1: 256, 2: 256, 3: 128, 4: 64}.get(variant, 64)
     if N % need:
         pytest.skip("N not a multiple of this variant's tile")
+    if variant == 5 and M > 8:
+        pytest.skip("the GEMV variant handles M <= 8")
     a, w, b = rnd(M, K, scale=0.5, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3)
     out = ops.gemm(a, w, b, variant=variant)
     assert rel(out, F.linear(a, w, b)) <= 1e-3
@@ -502,3 +504,17 @@ def test_rmsnorm_kernel_variants_bit_equal(kernel, rows, d, B):
         lib.flite_set_tuning(0, 0)
     assert torch.equal(y[:rows], base) and bool((y[rows:] == 7.0).all())
     assert torch.equal(y2, ops.rmsnorm_modulate(x, w, 2))
+
+
+def test_gemv_skinny_gemm_matches_tensor_core_variant():
+    """M <= 8 (timestep MLP / adaLN modulation): the weight-streaming GEMV that FLITE_GEMM_AUTO picks and the tcgen05
+    tile variant agree to fp32-accumulation-order noise (<= 1 bf16 ulp on a few outputs), bias + SiLU included."""
+    from flite_b200 import ops
+    for (M, N, K) in [(2, 12288, 3072), (2, 3072, 12288), (2, 6144, 3072), (5, 640, 512)]:
+        a, w, b = rnd(M, K, scale=0.5, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(N, seed=3)
+        for act in (0, 1):
+            g = ops.gemm(a, w, b, act=act, variant=5)
+            t = ops.gemm(a, w, b, act=act, variant=3)
+            auto = ops.gemm(a, w, b, act=act)
+            assert torch.equal(auto, g)                       # AUTO routes skinny shapes to the GEMV
+            assert rel(g, t) <= 2e-3 and (g == t).float().mean().item() > 0.98
