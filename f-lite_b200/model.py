@@ -177,6 +177,7 @@ class DiT(nn.Module):
         self._rope_cache = {}
         self._ws = {}
         self._gu_cache = {}
+        self._kvcat_cache = None
         self._ctx_cache = None
         self._freqs = None
         self.hoist_context = True
@@ -259,6 +260,21 @@ class DiT(nn.Module):
             self._gu_cache[i] = hit
         return hit[1]
 
+    def _context_kv_cat(self, cross):
+        """[K rows of every cross block ; V rows of every cross block] (+ bias), cached until a parameter changes."""
+        lins = [self.blocks[i].cross_attn.context_kv for i in cross]
+        key = tuple((l.weight.data_ptr(), l.weight._version, None if l.bias is None else l.bias._version) for l in lins)
+        hit = self._kvcat_cache
+        if hit is None or hit[0] != key:
+            d = self.config.hidden_size
+            w = torch.cat([l.weight.detach()[:d] for l in lins] + [l.weight.detach()[d:] for l in lins]).contiguous()
+            b = None
+            if lins[0].bias is not None:
+                b = torch.cat([l.bias.detach()[:d] for l in lins] + [l.bias.detach()[d:] for l in lins]).contiguous()
+            hit = (key, w, b)
+            self._kvcat_cache = hit
+        return hit[1], hit[2]
+
     def _buf(self, name, shape, device):
         key = (name, tuple(shape))
         b = self._ws.get(key)
@@ -284,13 +300,17 @@ class DiT(nn.Module):
         else:
             mask_f = mask.to(torch.float32)
         packed, cu_k = ops.pack_context(c.view(B, Lc, d), mask_f)
+        # context_kv of ALL cross-attention blocks in one GEMM (model.py:190-195 runs one Linear(d, 2d) per block): the
+        # weights are concatenated once as [K rows of every block ; V rows of every block], so that the QK-norm columns
+        # are the leading ones and block j's K / V are column slices j*d and (X + j)*d of one [Tc, 2*X*d] buffer.
+        cross = [i for i, blk in enumerate(self.blocks) if blk.cross_attn is not None]
         kvs = {}
-        for i, blk in enumerate(self.blocks):
-            if blk.cross_attn is None:
-                continue
-            lin = blk.cross_attn.context_kv
-            kvs[i] = ops.gemm(packed, lin.weight, lin.bias, epilogue=EPI_QKV_ROPE, qk_cols=d,
-                              variant=self.gemm_variant)
+        if cross:
+            X = len(cross)
+            wcat, bcat = self._context_kv_cat(cross)
+            kv_all = ops.gemm(packed, wcat, bcat, epilogue=EPI_QKV_ROPE, qk_cols=X * d, variant=self.gemm_variant)
+            for j, i in enumerate(cross):
+                kvs[i] = (kv_all[:, j * d:(j + 1) * d], kv_all[:, (X + j) * d:(X + j + 1) * d])
         return SimpleNamespace(kvs=kvs, cu_k=cu_k, B=B, Lc=Lc)
 
     def _context(self, context, mask):
@@ -436,8 +456,8 @@ class DiT(nn.Module):
                 ops.rmsnorm_modulate(xs, blk.norm2.weight, 1, scale_ca, shift_ca, rows_per_sample=Lq, out=nbuf)
                 ops.gemm(nbuf, ca.q.weight, ca.q.bias, epilogue=EPI_QKV_ROPE, qk_cols=d, rows_per_sample=Lq,
                          variant=v, out=qc)
-                kv = ctx.kvs[i]
-                ops.attention_varlen(qc, kv[:, :d], kv[:, d:], cu_x, ctx.cu_k, nh, Lq, scale, out=abuf)
+                ck, cv = ctx.kvs[i]
+                ops.attention_varlen(qc, ck, cv, cu_x, ctx.cu_k, nh, Lq, scale, out=abuf)
                 ops.gemm(abuf, ca.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_ca,
                          rows_per_sample=Lq, variant=v, out=xs)
             # ---- SwiGLU MLP (model.py:299-301)
