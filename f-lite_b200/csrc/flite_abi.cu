@@ -627,6 +627,9 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
     }
     if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_QTMEM_2WG)
         return fail(FLITE_ERR_INVALID, "attention: unknown variant %d", variant);
+    // short key sequences (cross-attention over the text context: <= 512 keys per sequence on average) may use their own variant
+    if (variant == FLITE_ATTN_AUTO && !peers && rows_k <= 512ll * B && g_tuning[FLITE_TUNE_ATTN_VARIANT_SHORT_K])
+        variant = g_tuning[FLITE_TUNE_ATTN_VARIANT_SHORT_K];
     if (variant == FLITE_ATTN_AUTO) variant = g_tuning[FLITE_TUNE_ATTN_VARIANT] ? g_tuning[FLITE_TUNE_ATTN_VARIANT] : FLITE_ATTN_2CTA_1WG_PTMEM;
     const bool cg2 = variant >= FLITE_ATTN_2CTA_1WG && variant <= FLITE_ATTN_2CTA_2WG_PTMEM;
     const bool qtmem = variant == FLITE_ATTN_QTMEM_1WG || variant == FLITE_ATTN_QTMEM_2WG;

@@ -69,6 +69,7 @@ extern "C" {
 #define FLITE_TUNE_GEMM_HINT_A 9      /* L2 eviction hint of the GEMM's A-tile TMA loads: 0 auto | 1 none | 2 evict_first | 3 evict_last */
 #define FLITE_TUNE_GEMM_HINT_B 10     /* same for the W-tile loads */
 #define FLITE_TUNE_PATCH_EMBED 11     /* 0 auto: patchify = gather + tcgen05 GEMM when C*P*P % 64 == 0 | 1 CUDA-core patch_embed kernel */
+#define FLITE_TUNE_ATTN_VARIANT_SHORT_K 12 /* attention variant for FLITE_ATTN_AUTO calls with <= 512 keys per sequence on average (cross-attention); 0 = same as the long-key default */
 #define FLITE_TUNE_GEMM_BAND 5       /* 0 = L2-aware band rasterisation for large M (default), 1 = single band */
 int flite_set_tuning(int key, int value);
 int flite_get_tuning(int key);   /* current value of a knob (0 for an unknown key) */
