@@ -617,6 +617,12 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
     if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || q_col0 % 8 || k_col0 % 8 || v_col0 % 8)
         return fail(FLITE_ERR_INVALID, "attention: strides / column offsets must be multiples of 8");
     if (B <= 0 || H <= 0 || max_q <= 0 || rows_q <= 0) return 0;
+    // Declared width of the q / k / v tensor maps = exactly the columns the kernels address (col0 + H heads of 256), NOT
+    // the row stride: q, k, v are usually column-offset views of a wider projection buffer, and a map that claims `ld`
+    // columns from the view's first element would extend past the end of the allocation in its last row.
+    const int64_t q_cols = (int64_t)q_col0 + 256ll * H, k_cols = (int64_t)k_col0 + 256ll * H, v_cols = (int64_t)v_col0 + 256ll * H;
+    if (q_cols > ldq || k_cols > ldk || v_cols > ldv)
+        return fail(FLITE_ERR_INVALID, "attention: col0 + 256*H exceeds the row stride");
     static bool configured = false;
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
@@ -667,11 +673,11 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
             xres_configured = true;
         }
         CUtensorMap xq, xk, xv;
-        int rcx = make_tmap(&xq, q, (uint64_t)rows_q, (uint64_t)ldq, (uint64_t)ldq, 128);
+        int rcx = make_tmap(&xq, q, (uint64_t)rows_q, (uint64_t)q_cols, (uint64_t)ldq, 128);
         if (rcx) return rcx;
-        rcx = make_tmap(&xk, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldk, (uint64_t)ldk, 128);
+        rcx = make_tmap(&xk, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)k_cols, (uint64_t)ldk, 128);
         if (rcx) return rcx;
-        rcx = make_tmap(&xv, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldv, (uint64_t)ldv, 128);
+        rcx = make_tmap(&xv, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)v_cols, (uint64_t)ldv, 128);
         if (rcx) return rcx;
         XresParams xp;
         xp.cu_q = cu_q; xp.cu_k = cu_k; xp.out = (__nv_bfloat16*)out; xp.ldo = ldo;
@@ -694,9 +700,9 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
     }
     if (qtmem) {
         CUtensorMap tk2, tv2;
-        int rc2 = make_tmap(&tk2, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldk, (uint64_t)ldk, 32);
+        int rc2 = make_tmap(&tk2, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)k_cols, (uint64_t)ldk, 32);
         if (rc2) return rc2;
-        rc2 = make_tmap(&tv2, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldv, (uint64_t)ldv, 64);
+        rc2 = make_tmap(&tv2, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)v_cols, (uint64_t)ldv, 64);
         if (rc2) return rc2;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * ((q_tiles + 1) / 2), H, B);
@@ -717,11 +723,11 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
         return 0;
     }
     CUtensorMap tq, tk, tv;
-    int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)ldq, (uint64_t)ldq, 128);
+    int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)q_cols, (uint64_t)ldq, 128);
     if (rc) return rc;
-    rc = make_tmap(&tk, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldk, (uint64_t)ldk, cg2 ? 64 : 128);
+    rc = make_tmap(&tk, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)k_cols, (uint64_t)ldk, cg2 ? 64 : 128);
     if (rc) return rc;
-    rc = make_tmap(&tv, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)ldv, (uint64_t)ldv, 128);
+    rc = make_tmap(&tv, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)v_cols, (uint64_t)ldv, 128);
     if (rc) return rc;
     if (!cg2) {
         dim3 grid(q_tiles, H, B);
