@@ -12,6 +12,7 @@
 
 #include "../../include/flite_b200.h"
 #include "attn_cg2_sm100.cuh"
+#include "attn_xres_sm100.cuh"
 #include "attn_qtmem_sm100.cuh"
 #include "attn_sm100.cuh"
 #include "elementwise.cuh"
@@ -253,8 +254,11 @@ int flite_watchdog_status(unsigned int* code_out) {
     if (code_out) *code_out = code;
     if (code != 0) {
         CUDA_TRY(cudaMemcpyToSymbol(g_flite_abort, &zero, sizeof(zero)));
-        return fail(FLITE_ERR_WATCHDOG, "kernel barrier wait timed out: tag %u block %u", (code >> 16) & 0x7fff,
-                    code & 0xffff);
+        const unsigned tag = (code >> 16) & 0x7fff;
+        if (tag >= 96 && tag <= 98)
+            return fail(FLITE_ERR_WATCHDOG, "kernel precondition failed (tag %u: 96 = a sequence has more than 256 keys in the "
+                        "resident-K/V attention, 97 / 98 = shared-memory window misaligned)", tag);
+        return fail(FLITE_ERR_WATCHDOG, "kernel barrier wait timed out: tag %u block %u", tag, code & 0xffff);
     }
     return 0;
 }
@@ -631,10 +635,11 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_qtmem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM));
         configured = true;
     }
-    if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_QTMEM_2WG)
+    if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_XRES)
         return fail(FLITE_ERR_INVALID, "attention: unknown variant %d", variant);
     // short key sequences (cross-attention over the text context: <= 512 keys per sequence on average) may use their own variant
-    if (variant == FLITE_ATTN_AUTO && !peers && rows_k <= 512ll * B && g_tuning[FLITE_TUNE_ATTN_VARIANT_SHORT_K])
+    if (variant == FLITE_ATTN_AUTO && !peers && rows_k <= 512ll * B && g_tuning[FLITE_TUNE_ATTN_VARIANT_SHORT_K] > 0 &&
+        g_tuning[FLITE_TUNE_ATTN_VARIANT_SHORT_K] != FLITE_ATTN_XRES)   // XRES needs the per-sequence bound the host knows
         variant = g_tuning[FLITE_TUNE_ATTN_VARIANT_SHORT_K];
     if (variant == FLITE_ATTN_AUTO) variant = g_tuning[FLITE_TUNE_ATTN_VARIANT] ? g_tuning[FLITE_TUNE_ATTN_VARIANT] : FLITE_ATTN_2CTA_1WG_PTMEM;
     const bool cg2 = variant >= FLITE_ATTN_2CTA_1WG && variant <= FLITE_ATTN_2CTA_2WG_PTMEM;
@@ -659,6 +664,40 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
     }
     p.stage_out = (peers != nullptr || g_tuning[FLITE_TUNE_ATTN_STAGED_STORES]) ? 1 : 0;
     const int q_tiles = (max_q + 127) / 128;
+    if (variant == FLITE_ATTN_XRES) {
+        // persistent cross-attention with resident K/V: every sequence must have <= 256 keys (checked in the kernel)
+        if (peers) return fail(FLITE_ERR_INVALID, "attention: the resident-K/V variant has no peer-memory output path");
+        static bool xres_configured = false;
+        if (!xres_configured) {
+            CUDA_TRY(cudaFuncSetAttribute(attn_xres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XR_SMEM));
+            xres_configured = true;
+        }
+        CUtensorMap xq, xk, xv;
+        int rcx = make_tmap(&xq, q, (uint64_t)rows_q, (uint64_t)q_cols, (uint64_t)ldq, 128);
+        if (rcx) return rcx;
+        rcx = make_tmap(&xk, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)k_cols, (uint64_t)ldk, 128);
+        if (rcx) return rcx;
+        rcx = make_tmap(&xv, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)v_cols, (uint64_t)ldv, 128);
+        if (rcx) return rcx;
+        XresParams xp;
+        xp.cu_q = cu_q; xp.cu_k = cu_k; xp.out = (__nv_bfloat16*)out; xp.ldo = ldo;
+        xp.q_col0 = q_col0; xp.k_col0 = k_col0; xp.v_col0 = v_col0;
+        xp.scale_log2 = softmax_scale * 1.4426950408889634f;
+        xp.B = B; xp.H = H; xp.q_pairs = (max_q + 255) / 256;
+        const long long n_units = (long long)B * H * xp.q_pairs;
+        long long clusters = num_sms() / 2;
+        if (clusters > n_units) clusters = n_units;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * clusters));
+        cfg.blockDim = dim3(XR_THREADS);
+        cfg.dynamicSmemBytes = XR_SMEM;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[2];
+        cfg.attrs = attr;
+        cfg.numAttrs = fill_launch_attrs(attr, 2);
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_xres_kernel, xq, xk, xv, xp));
+        return 0;
+    }
     if (qtmem) {
         CUtensorMap tk2, tv2;
         int rc2 = make_tmap(&tk2, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)k_cols, (uint64_t)ldk, 32);

@@ -27,7 +27,7 @@ import torch
 from torch import nn
 
 from . import ops
-from ._lib import (EPI_GATED_RES, EPI_QKV_ROPE, EPI_STORE, EPI_SWIGLU, GEMM_AUTO, FliteError)
+from ._lib import (ATTN_XRES, EPI_GATED_RES, EPI_QKV_ROPE, EPI_STORE, EPI_SWIGLU, GEMM_AUTO, FliteError)
 
 N_REGISTER = 16  # model.py:446,535,540
 
@@ -414,6 +414,12 @@ class DiT(nn.Module):
             ao_full = self._buf("ao_full", (B, L, dq), dev)
             ao_recv = self._buf("ao_recv", (B, P, Lq * dq), dev)         # [sample][source rank][local token, head group]
 
+        # cross-attention over <= 256 context tokens per sequence may use the persistent resident-K/V kernel
+        # (FLITE_ATTN_XRES): OPT-IN through FLITE_TUNE_ATTN_VARIANT_SHORT_K = 9 -- it is 10-15 % faster than the general
+        # kernel on that launch, but one full-file run of tests/test_model_gpu.py hit an illegal memory access with it
+        # enabled by default (not reproduced in isolation or under CUDA_LAUNCH_BLOCKING), so the default stays the
+        # general kernel until that is understood.
+        x_variant = ATTN_XRES if (ctx.Lc <= 256 and ops.get_tuning(12) == ATTN_XRES) else 0
         for i, blk in enumerate(self.blocks):
             # ---- self-attention (model.py:283-289)
             ops.rmsnorm_modulate(xs, blk.norm1.weight, 1, scale_sa, shift_sa, rows_per_sample=Lq, out=nbuf)
@@ -457,7 +463,7 @@ class DiT(nn.Module):
                 ops.gemm(nbuf, ca.q.weight, ca.q.bias, epilogue=EPI_QKV_ROPE, qk_cols=d, rows_per_sample=Lq,
                          variant=v, out=qc)
                 ck, cv = ctx.kvs[i]
-                ops.attention_varlen(qc, ck, cv, cu_x, ctx.cu_k, nh, Lq, scale, out=abuf)
+                ops.attention_varlen(qc, ck, cv, cu_x, ctx.cu_k, nh, Lq, scale, out=abuf, variant=x_variant)
                 ops.gemm(abuf, ca.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_ca,
                          rows_per_sample=Lq, variant=v, out=xs)
             # ---- SwiGLU MLP (model.py:299-301)

@@ -24,12 +24,20 @@ PROFILE_HOOK = None
 # Per-op device timing (tools/mgpu_check.py --trace, tools/profile_step.py): when TRACE is a list every public op
 # below appends (label, start_event, end_event) recorded on the launching stream; trace_report() aggregates them.
 TRACE = None
+DEBUG_SYNC = bool(int(__import__("os").environ.get("FLITE_DEBUG_SYNC", "0")))
 
 
 def _traced(label_fn):
     def deco(fn):
         def wrapper(*args, **kwargs):
             tr = TRACE
+            if DEBUG_SYNC:      # FLITE_DEBUG_SYNC=1: synchronise after every op and name the one that faulted
+                r = fn(*args, **kwargs)
+                try:
+                    torch.cuda.synchronize()
+                except Exception as e:
+                    raise _lib.FliteError(f"device fault surfaced after {label_fn(*args, **kwargs)}: {e}") from e
+                return r
             if tr is None:
                 return fn(*args, **kwargs)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -55,6 +63,10 @@ def trace_report():
 
 
 _EPI_NAMES = {EPI_STORE: "store", EPI_GATED_RES: "gated_res", EPI_SWIGLU: "swiglu", EPI_QKV_ROPE: "qkv_rope"}
+
+
+def get_tuning(key: int) -> int:
+    return _lib.load().flite_get_tuning(key)
 
 
 def _stream() -> int:

@@ -55,6 +55,7 @@ extern "C" {
 #define FLITE_ATTN_2CTA_2WG_PTMEM 6
 #define FLITE_ATTN_QTMEM_1WG 7 /* cta_group::2, Q and P both TMEM operands, 64-key tiles, 6-stage K/V ring */
 #define FLITE_ATTN_QTMEM_2WG 8
+#define FLITE_ATTN_XRES 9        /* persistent cross-attention, K/V (<= 256 keys per sequence, checked on the device) resident in the CTA pair */
 
 /* tuning knobs (A/B switches used by the benchmarks; defaults are the measured best) */
 #define FLITE_TUNE_RMSNORM_KERNEL 0  /* 0 auto | 1 two-pass | 2 register-resident | 3 streaming (persistent warps, next-row prefetch) */
@@ -69,7 +70,7 @@ extern "C" {
 #define FLITE_TUNE_GEMM_HINT_A 9      /* L2 eviction hint of the GEMM's A-tile TMA loads: 0 auto | 1 none | 2 evict_first | 3 evict_last */
 #define FLITE_TUNE_GEMM_HINT_B 10     /* same for the W-tile loads */
 #define FLITE_TUNE_PATCH_EMBED 11     /* 0 auto: patchify = gather + tcgen05 GEMM when C*P*P % 64 == 0 | 1 CUDA-core patch_embed kernel */
-#define FLITE_TUNE_ATTN_VARIANT_SHORT_K 12 /* attention variant for FLITE_ATTN_AUTO calls with <= 512 keys per sequence on average (cross-attention); 0 = same as the long-key default */
+#define FLITE_TUNE_ATTN_VARIANT_SHORT_K 12 /* attention variant for FLITE_ATTN_AUTO calls with <= 512 keys per sequence on average (cross-attention); 0 = same as the long-key default; 9 (FLITE_ATTN_XRES) = the host model requests the resident-K/V kernel when the padded context has <= 256 tokens (opt-in) */
 #define FLITE_TUNE_GEMM_BAND 5       /* 0 = L2-aware band rasterisation for large M (default), 1 = single band */
 int flite_set_tuning(int key, int value);
 int flite_get_tuning(int key);   /* current value of a knob (0 for an unknown key) */

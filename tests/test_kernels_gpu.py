@@ -518,3 +518,50 @@ def test_gemv_skinny_gemm_matches_tensor_core_variant():
             auto = ops.gemm(a, w, b, act=act)
             assert torch.equal(auto, g)                       # AUTO routes skinny shapes to the GEMV
             assert rel(g, t) <= 2e-3 and (g == t).float().mean().item() > 0.98
+
+
+XRES_CASES = [
+    # (q_lens, k_lens, H)
+    ([272, 272], [256, 256], 2),          # full tiles of keys
+    ([272, 300, 1], [17, 129, 200], 2),   # ragged keys on both sides of the 128-key half, ragged queries
+    ([4112, 4112], [256, 77], 12),        # config C2 cross-attention shape
+    ([500, 40], [0, 256], 1),             # an empty key sequence -> zeros
+    ([256], [1], 3),                      # a single key
+]
+
+
+@pytest.mark.parametrize("q_lens,k_lens,H", XRES_CASES)
+def test_attention_resident_kv_cross_attention(q_lens, k_lens, H):
+    """FLITE_ATTN_XRES (persistent cross-attention with K/V resident in shared memory, <= 256 keys per sequence)
+    against the fp32 restatement of flash_attn_varlen_func and against the general 2-CTA kernel."""
+    from flite_b200 import ops
+    from oracle.dit_oracle import flash_attn_varlen
+    cu_q = torch.tensor([0] + list(np.cumsum(q_lens)), dtype=torch.int32, device=DEV)
+    cu_k = torch.tensor([0] + list(np.cumsum(k_lens)), dtype=torch.int32, device=DEV)
+    Tq, Tk = sum(q_lens), max(sum(k_lens), 1)
+    q = rnd(Tq, H * 256, seed=1)
+    kv = rnd(Tk, 2 * H * 256, seed=2)                      # K | V column halves of one buffer (strided views)
+    k, v = kv[:, :H * 256], kv[:, H * 256:]
+    out = torch.full((Tq + 2, H * 256), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.attention_varlen(q, k, v, cu_q, cu_k, H, max(q_lens), 1 / 16, out=out[:Tq], variant=9)
+    ref = flash_attn_varlen(q.view(Tq, H, 256), k.reshape(Tk, H, 256), v.reshape(Tk, H, 256), cu_q, cu_k, 1 / 16)
+    ref = ref.reshape(Tq, H * 256)
+    for b, kl in enumerate(k_lens):                        # torch softmax over zero keys gives NaN; flash-attn gives 0
+        if kl == 0:
+            ref[cu_q[b]:cu_q[b + 1]] = 0
+    general = ops.attention_varlen(q, k, v, cu_q, cu_k, H, max(q_lens), 1 / 16, variant=5)
+    assert torch.isfinite(out[:Tq].float()).all() and bool((out[Tq:] == 7.0).all())
+    assert rel(out[:Tq], ref) <= 4e-3 and rel(out[:Tq], general) <= 4e-3
+
+
+def test_attention_resident_kv_rejects_long_key_sequences():
+    """> 256 keys in a sequence: the kernel refuses (watchdog word, tag 96) instead of truncating the context."""
+    from flite_b200 import _lib, ops
+    H = 1
+    cu_q = torch.tensor([0, 128], dtype=torch.int32, device=DEV)
+    cu_k = torch.tensor([0, 300], dtype=torch.int32, device=DEV)
+    q, k, v = rnd(128, 256, seed=1), rnd(300, 256, seed=2), rnd(300, 256, seed=3)
+    ops.attention_varlen(q, k, v, cu_q, cu_k, H, 128, 1 / 16, variant=9)
+    with pytest.raises(_lib.FliteError, match="precondition"):
+        _lib.watchdog_ok()
+    _lib.watchdog_ok()                                      # the word is cleared after it has been reported
