@@ -65,6 +65,17 @@ def test_bad_arguments_return_error_codes():
                                1e-6, 0, 0, 0, None) == -1
     assert b"K = 63" in lib.flite_last_error()
     assert lib.flite_cfg_euler(one, 0, one, one, 6.0, 0.1, 1, one, 12, None) == -1
+    # attention: the q / k / v views must hold col0 + 256*H columns inside their row stride (the tensor maps declare
+    # exactly that width; a map wider than the view would reach past the end of the buffer)
+    assert lib.flite_attention_varlen(one, 512, 128, 0, one, 512, 128, 0, one, 512, 0, one, 512, one, one, 1, 3, 128,
+                                      0.0625, 0, None) == -1
+    assert b"row stride" in lib.flite_last_error()
+    assert lib.flite_attention_varlen(one, 768, 128, 0, one, 768, 128, 8, one, 768, 0, one, 768, one, one, 1, 3, 128,
+                                      0.0625, 0, None) == -1                      # k_col0 = 8 pushes K past its stride
+    assert lib.flite_apg_euler(one, 0, one, one, 6.0, 0.1, 0.03, one, 8, one, None) == -1   # numel must exceed 8
+    assert lib.flite_latent_unscale(one, one, 0.0, 0.1, 16, None) == -1                     # zero scaling factor
+    assert lib.flite_gemm_bf16(one, 64, one, 64, one, 64, 16, 64, 64, None, 0, 0, None, 0, None, 0, 0, None, None, 0,
+                               1e-6, 0, 0, 5, None) == -1                                   # GEMV variant needs M <= 8
 
 
 @pytest.mark.parametrize("cfg", [synth.TINY, dict(synth.TINY, depth=9, train_bias_and_rms=False)])
