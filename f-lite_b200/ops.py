@@ -5,6 +5,7 @@ sm_100a kernel from ``libflite_b200.so`` on torch's current CUDA stream.  No fal
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -24,14 +25,17 @@ PROFILE_HOOK = None
 # Per-op device timing (tools/mgpu_check.py --trace, tools/profile_step.py): when TRACE is a list every public op
 # below appends (label, start_event, end_event) recorded on the launching stream; trace_report() aggregates them.
 TRACE = None
-DEBUG_SYNC = bool(int(__import__("os").environ.get("FLITE_DEBUG_SYNC", "0")))
+# FLITE_DEBUG_SYNC=1 (or ops.DEBUG_SYNC = True around a region): synchronise after every op and raise naming the op
+# after which a device fault surfaced -- how the layout-dependent TMA fault of DESIGN.md section 7 was located.  Not
+# usable under CUDA-graph capture (synchronising is illegal there).
+DEBUG_SYNC = bool(int(os.environ.get("FLITE_DEBUG_SYNC", "0")))
 
 
 def _traced(label_fn):
     def deco(fn):
         def wrapper(*args, **kwargs):
             tr = TRACE
-            if DEBUG_SYNC:      # FLITE_DEBUG_SYNC=1: synchronise after every op and name the one that faulted
+            if DEBUG_SYNC:
                 r = fn(*args, **kwargs)
                 try:
                     torch.cuda.synchronize()
