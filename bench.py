@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- F Lite denoise steps/s on B200 (BASELINE.json metric), one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4|c5]
 
 A "step" is one denoise step of the reference sampler: one CFG-batched DiT forward on [negative, positive]
 (f_lite/pipeline.py:264-271 with the 4-argument forward of f_lite/model.py:526) + CFG combine + Euler update
@@ -11,14 +11,28 @@ text context 256 tokens of width 4096, bf16, synthetic latents/embeddings, rando
 For N>1 every rank runs its own image (data parallel over prompts, no collective on the data path): weak scaling,
 value = N images' steps per second.
 
-Printed JSON keys follow the driver contract: value (inputs resident in HBM), e2e (host buffers, H2D/D2H inside the
-timed region, through flite_b200.denoise_step = the public API), roofline (dominant kernel = MLP gate/up tcgen05 GEMM,
-CUDA events on the launching stream during the timed region), cpu_baseline (oracle port of the reference on the host
-cores, bounded sample), clocks, gpu_launches.
+Our arm (default).  Printed JSON keys follow the driver contract: value (inputs resident in HBM), e2e (host buffers,
+H2D/D2H inside the timed region, through flite_b200.denoise_step = the public API), roofline (dominant kernel = MLP
+gate/up tcgen05 GEMM, CUDA events on the launching stream during the timed region; traffic read from the newest
+profiles/*ncu_full*.csv), cpu_baseline (N=1 only; bounded sample of the same workload on the host cores), clocks,
+gpu_launches.  Extra keys: `c1` (BASELINE.json configs[0] run in full on this GPU: 4 Euler steps of the tiny DiT) and,
+for N>1, `multi_gpu` -- the COMMUNICATING layouts of SURVEY.md 8(e) run after the data-parallel timing with the same
+weights: CFG halves on two GPUs (C2) and Ulysses sequence parallelism with the exchange fused into the kernels over
+NVLink peer memory (C4, one 2048^2 image), each with ms/step (max over ranks), speed-up over the 1-GPU step measured in
+the same process, and rel-L2 of the step's result against the 1-GPU path (0.0 = bit-identical).
+
+Reference arm (--impl reference; rank 0 only).  The UNMODIFIED reference module (oracle/_ref/f_lite/model.py, installed
+by oracle/build_ref.py) on the host cores: `value` = C2 steps/s from a bounded sample per step (one cross-attention
+DiTBlock + one plain DiTBlock of the reference's own classes at the full C2 token count, scaled to the 16 + 24 block
+mix; ms_per_step is the time actually measured per sample), plus `c1_full` (configs[0] run in full, nothing
+extrapolated) and `reference_gpu` (the same unmodified module in bf16 on the B200 with the real liger_kernel and
+flash-attn 2 kernels at C2 -- what the reference itself would run on this box).
 """
 from __future__ import annotations
 
 import argparse
+import csv
+import glob
 import json
 import math
 import os
@@ -41,9 +55,10 @@ WORKLOADS = {
     "c2": (ARCH_10B, 1024, 1024, 256, 1),
     "c1": (ARCH_TINY, 256, 256, 256, 1),
     "c3": (ARCH_7B, 1344, 896, 256, 8),     # 64 prompts over 8 GPUs = 8 images (16 CFG sequences) per GPU
-    "c4": (ARCH_10B, 2048, 2048, 256, 1),   # single 2048^2 image (1-GPU form; Ulysses form: tools/mgpu_check.py)
-    "c5": (ARCH_10B, 1024, 1024, 256, 4),   # batch 32 over 8 GPUs = 4 images per GPU (VAE decode not included)
+    "c4": (ARCH_10B, 2048, 2048, 256, 1),   # single 2048^2 image (1-GPU form; Ulysses form: `multi_gpu` key at N>1)
+    "c5": (ARCH_10B, 1024, 1024, 256, 4),   # batch 32 over 8 GPUs = 4 images per GPU (with decode: tools/pipeline_bench.py)
 }
+GUIDANCE = 6.0
 
 
 def flops_per_step(cfg, height, width, ctx_len, images):
@@ -71,16 +86,78 @@ def measured_peaks():
     return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def workload_desc(name, cfg, height, width, ctx_len, images, n_gpus):
+    L = 16 + (height // 16) * (width // 16)
+    return (f"{name.upper()}: F Lite DiT d{cfg['hidden_size']} depth{cfg['depth']} heads{cfg['num_heads']} "
+            f"{height}x{width}, CFG-batched [neg,pos] => {2 * images} seq x {L} tokens per GPU, ctx {ctx_len}x"
+            f"{cfg['cross_attn_input_size']}, {images} image(s)/GPU x {n_gpus} GPU(s)")
+
+
+def bench_config(name, cfg, height, width, ctx_len, images, n_gpus):
+    """The `config` object -- built by ONE function so both arms print the same thing for the same flags."""
+    return {"workload": workload_desc(name, cfg, height, width, ctx_len, images, n_gpus),
+            "parallelism": f"dp{n_gpus} (one image set per GPU, no data-path collective)",
+            "weights": "random-init, de-zeroed (seed 0), replicated per GPU",
+            "context_kv": "recomputed every step (hoisting disabled)",
+            "l2": "GBs of weights streamed per step >> 126 MB L2, no flush needed",
+            "flops_per_step_per_gpu": flops_per_step(cfg, height, width, ctx_len, images)}
+
+
+def ncu_traffic(kernel_substr, grid_hint=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the first kernel whose name contains `kernel_substr`,
+    from the newest profiles/*ncu_full*.csv (an `ncu -i ... --page raw --csv` export).  Returns (bytes, file) or
+    (None, None) -- never a hard-coded number."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_full*.csv")), key=os.path.getmtime, reverse=True)
+    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in files:
+        try:
+            rows = list(csv.reader(open(path, newline="")))
+        except Exception:
+            continue
+        hdr = next((i for i, r in enumerate(rows) if "Kernel Name" in r), None)
+        if hdr is None or hdr + 2 >= len(rows):
+            continue
+        names, units = rows[hdr], rows[hdr + 1]
+        try:
+            kn, rd, wr = names.index("Kernel Name"), names.index("dram__bytes_read.sum"), names.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        for r in rows[hdr + 2:]:
+            if len(r) <= max(kn, rd, wr) or kernel_substr not in r[kn]:
+                continue
+            if grid_hint is not None and grid_hint not in ",".join(r):
+                continue
+            try:
+                total = (float(r[rd].replace(",", "")) * unit_scale.get(units[rd], 1.0)
+                         + float(r[wr].replace(",", "")) * unit_scale.get(units[wr], 1.0))
+            except ValueError:
+                continue
+            return total, os.path.relpath(path, ROOT)
+    return None, None
+
+
 # --------------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the reference's CPU path (bounded sample of the same workload)
+# reference arm / cpu_baseline: the UNMODIFIED reference module on the host cores
 # --------------------------------------------------------------------------------------------------------------
+def _dezero_(module, seed):
+    """Seeded de-zeroed default init for a reference module (f_lite/model.py zero-inits adaLN / final layers, D10)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    for name, p in module.named_parameters():
+        if p.abs().sum().item() == 0:
+            p.data.copy_(torch.randn(p.shape, generator=g) * 0.02)
+
+
 def cpu_reference_sample(cfg, height, width, ctx_len, images, repeats=1):
-    """Times the reference algorithm (oracle/dit_oracle.py, torch fp32 on all host cores) on a bounded sample of the
-    step: ONE cross-attention block + ONE plain block at the workload's full token count, and scales to the step's
-    block mix.  The embedders and the final head (< 0.1 % of the FLOPs) are not sampled."""
+    """Bounded sample of one C-workload step on the host cores with the reference's OWN classes: one
+    `DiTBlock(do_cross_attn=True)` + one `DiTBlock(do_cross_attn=False)` of the unmodified f_lite/model.py (fp32, all
+    host threads; LigerRMSNorm / LigerSwiGLUMLP / flash_attn_varlen_func are Triton / CUDA-only, so on the CPU they are
+    the torch restatements of oracle/dit_oracle.py) at the workload's full token count, scaled to the step's block
+    mix.  The embedders and the final head (< 0.1 % of the FLOPs) are not sampled.
+    Returns (extrapolated step seconds per repeat, measured sample seconds per repeat, cores, kind, description)."""
     import torch
 
-    from oracle import dit_oracle, synth
+    from oracle import build_ref, dit_oracle
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -88,18 +165,8 @@ def cpu_reference_sample(cfg, height, width, ctx_len, images, repeats=1):
     B = 2 * images
     h, w = height // 8 // p, width // 8 // p
     L = 16 + h * w
-    scfg = dict(synth.TINY, **{k: cfg[k] for k in cfg})
-    scfg["depth"] = 2
-    # block 0 has cross-attention; the sampled "plain" block reuses blocks.1's weights without its cross branch
-    shapes = {k: v for k, v in synth.param_shapes(scfg).items() if k.startswith("blocks.")}
+    n_cross = len([i for i in range(depth) if i % 4 == 0 or i < 8])
     g = torch.Generator().manual_seed(0)
-    sd = {}
-    for k, shp in shapes.items():
-        if k.endswith("norm1.weight") or k.endswith("norm2.weight") or k.endswith("norm3.weight"):
-            sd[k] = torch.ones(shp)
-        else:
-            fan_in = shp[1] if len(shp) > 1 else d
-            sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan_in)
     x = torch.randn(B * L, d, generator=g)
     ctx = torch.randn(B * ctx_len, d, generator=g)
     cu_x = torch.arange(B + 1, dtype=torch.int32) * L
@@ -107,46 +174,171 @@ def cpu_reference_sample(cfg, height, width, ctx_len, images, repeats=1):
     mod = tuple(0.1 * torch.randn(B, d, generator=g).repeat_interleave(L, 0) for _ in range(9))
     cos, sin = dit_oracle.rope_tables(d // nh, h, w, 10000, "cpu", torch.float32)
     rope = (cos.repeat(1, B, 1), sin.repeat(1, B, 1))
-    n_cross = len([i for i in range(depth) if i % 4 == 0 or i < 8])
-    steps = []
+    if build_ref.ref_path("f_lite/model.py") is not None:
+        from oracle import ref_shim
+        m = ref_shim.load_reference_model_module("cpu")
+        torch.manual_seed(0)
+        blk_x = m.DiTBlock(d, nh, do_cross_attn=True, mlp_ratio=cfg["mlp_ratio"], qkv_bias=True).eval()
+        blk_p = m.DiTBlock(d, nh, do_cross_attn=False, mlp_ratio=cfg["mlp_ratio"], qkv_bias=True).eval()
+        run_x = lambda: blk_x(x, cu_x, L, ctx, cu_c, ctx_len, mod, rope)
+        run_p = lambda: blk_p(x, cu_x, L, ctx, cu_c, ctx_len, mod, rope)
+        kind, what = "reference", "f_lite/model.py::DiTBlock (unmodified, oracle/_ref)"
+    else:   # oracle/_ref not installed: the port
+        from oracle import synth
+        scfg = dict(synth.TINY, **{k: cfg[k] for k in cfg})
+        scfg["depth"] = 2
+        shapes = {k: v for k, v in synth.param_shapes(scfg).items() if k.startswith("blocks.")}
+        sd = {}
+        for k, shp in shapes.items():
+            if "norm" in k:
+                sd[k] = torch.ones(shp)
+            else:
+                fan_in = shp[1] if len(shp) > 1 else d
+                sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan_in)
+        run_x = lambda: dit_oracle.dit_block(sd, 0, x, cu_x, ctx, cu_c, mod, rope, nh, True, dit_oracle.flash_attn_varlen)
+        run_p = lambda: dit_oracle.dit_block(sd, 1, x, cu_x, ctx, cu_c, mod, rope, nh, False, dit_oracle.flash_attn_varlen)
+        kind, what = "port", "oracle/dit_oracle.py::dit_block (oracle/_ref not installed)"
+    full, sample = [], []
     with torch.no_grad():
         for _ in range(repeats):
             t0 = time.perf_counter()
-            dit_oracle.dit_block(sd, 0, x, cu_x, ctx, cu_c, mod, rope, nh, True, dit_oracle.flash_attn_varlen)
+            run_x()
             t1 = time.perf_counter()
-            dit_oracle.dit_block(sd, 1, x, cu_x, ctx, cu_c, mod, rope, nh, False, dit_oracle.flash_attn_varlen)
+            run_p()
             t2 = time.perf_counter()
-            steps.append(n_cross * (t1 - t0) + (depth - n_cross) * (t2 - t1))
-    sample = (f"per step: 1 cross-attention block ({t1 - t0:.2f} s) + 1 plain block ({t2 - t1:.2f} s) of the {depth}-block "
-              f"DiT at {B}x{L} tokens, fp32 torch on {cores} threads; step time = {n_cross}*cross + {depth - n_cross}*plain")
-    return steps, cores, sample
+            full.append(n_cross * (t1 - t0) + (depth - n_cross) * (t2 - t1))
+            sample.append(t2 - t0)
+    desc = (f"per step: 1 cross-attention block ({t1 - t0:.2f} s) + 1 plain block ({t2 - t1:.2f} s) of {what} at "
+            f"{B}x{L} tokens, fp32 torch on {cores} threads; full-step time = {n_cross}*cross + {depth - n_cross}*plain")
+    return full, sample, cores, kind, desc
+
+
+def cpu_reference_c1_full(steps=4, repeats=3):
+    """BASELINE.json configs[0] in FULL, nothing extrapolated: the unmodified reference DiT (tiny: d 512, depth 4),
+    256x256, 4 Euler steps, CFG 6 (batched [neg, pos]), batch 1, fp32 on all host cores, driven by the reference's
+    sampler loop as restated in oracle/sampler_oracle.py (f_lite/pipeline.py:244-297)."""
+    import torch
+
+    from oracle import build_ref, ref_shim, sampler_oracle
+    if build_ref.ref_path("f_lite/model.py") is None:
+        return {"unavailable": "oracle/_ref not installed"}
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    cfg = {k: v for k, v in ARCH_TINY.items()}
+    model = ref_shim.build_reference_dit(cfg, None, torch.float32, backend="cpu")
+    _dezero_(model, 0)
+    g = torch.Generator().manual_seed(1234)
+    lat = torch.randn(1, 16, 32, 32, generator=g)
+    pos = torch.randn(1, 256, 4096, generator=g)
+    neg = torch.zeros_like(pos)
+    mask = torch.ones(2, 256)
+    fn = lambda *a: model(*a)
+    times = []
+    for _ in range(repeats + 1):
+        t0 = time.perf_counter()
+        out = sampler_oracle.sample_pipeline(fn, lat, neg, pos, mask, steps, GUIDANCE)
+        times.append((time.perf_counter() - t0) / steps)
+    best = min(times[1:])
+    return {"config": "C1: tiny DiT d512 depth4 heads2, 256x256, 4 Euler steps, CFG 6, batch 1, fp32, unmodified "
+                      "f_lite/model.py (oracle/_ref) through the reference sampler loop",
+            "ms_per_step": best * 1e3, "steps_per_s": 1.0 / best, "cores": cores, "kind": "reference",
+            "finite": bool(torch.isfinite(out).all())}
+
+
+def reference_gpu_c2(cfg, height, width, ctx_len, images, steps, warmup=2):
+    """The unmodified reference module on the B200 in bf16 with the REAL third-party kernels (liger_kernel Triton
+    RMSNorm / SwiGLU, FlashAttention-2 behind the flash_attn_interface name) -- what the reference runs on this box.
+    One step = CFG-batched forward + the reference's own torch CFG / Euler ops (pipeline.py:290,296-297)."""
+    import torch
+    if not torch.cuda.is_available():
+        return {"unavailable": "no GPU visible"}
+    try:
+        from oracle import build_ref, ref_shim
+        if build_ref.ref_path("f_lite/model.py") is None:
+            return {"unavailable": "oracle/_ref not installed"}
+        import flash_attn
+        import liger_kernel
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.cuda.set_device(dev)
+        torch.manual_seed(0)
+        model = ref_shim.build_reference_dit(cfg, None, torch.bfloat16, backend="gpu", device=dev)
+        g = torch.Generator(device=dev).manual_seed(0)
+        for name, p in model.named_parameters():
+            if p.abs().sum().item() == 0:
+                p.data.copy_(torch.randn(p.shape, device=dev, generator=g) * 0.02)
+        b = images
+        lat = torch.randn((b, 16, height // 8, width // 8), device=dev, generator=g).bfloat16()
+        pos = torch.randn((b, ctx_len, cfg["cross_attn_input_size"]), device=dev, generator=g).bfloat16()
+        ctx = torch.cat([torch.zeros_like(pos), pos])
+        mask = torch.ones((2 * b, ctx_len), device=dev)
+        from flite_b200.pipeline import default_alpha, time_shift_schedule
+        sched = time_shift_schedule(30, default_alpha(height // 8, width // 8))
+
+        def step(i):
+            nonlocal lat
+            t, dt = sched[i % 30]
+            tt = torch.tensor([t] * (2 * b), device=dev, dtype=torch.bfloat16)
+            with torch.no_grad():
+                out = model(torch.cat([lat] * 2), ctx, mask, tt)
+            u, c = out.chunk(2)
+            lat = lat + dt * (u + GUIDANCE * (c - u))
+
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        fl = flops_per_step(cfg, height, width, ctx_len, images)
+        out = {"ms_per_step": ms, "steps_per_s": images * 1e3 / ms, "steps": steps, "warmup": warmup, "dtype": "bf16",
+               "tflops": fl / (ms * 1e-3) / 1e12, "finite": bool(torch.isfinite(lat.float()).all()),
+               "module": "unmodified f_lite/model.py (oracle/_ref), eager PyTorch",
+               "attention_backend": f"flash_attn {flash_attn.__version__} flash_attn_varlen_func (FA2; the reference "
+                                    "imports FA3's flash_attn_interface, Hopper-only and not installed)",
+               "norm_mlp_backend": f"liger_kernel {getattr(liger_kernel, '__version__', '0.8.0')} LigerRMSNorm / LigerSwiGLUMLP (Triton)",
+               "gemm_backend": f"torch {torch.__version__} nn.Linear (cuBLASLt)"}
+        del model
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:   # a missing / broken third-party kernel must not take the CPU line down with it
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
 
 
 def run_reference(args, cfg, height, width, ctx_len, images, workload_name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, cores, sample = cpu_reference_sample(cfg, height, width, ctx_len, images, repeats=args.warmup + args.steps)
-    times = steps[args.warmup:]
-    step_s = sum(times) / len(times)
-    val = 1.0 / step_s
+    full, sample, cores, kind, desc = cpu_reference_sample(cfg, height, width, ctx_len, images,
+                                                           repeats=args.warmup + args.steps)
+    full_t, sample_t = full[args.warmup:], sample[args.warmup:]
+    step_s = sum(full_t) / len(full_t)
+    sample_s = sum(sample_t) / len(sample_t)
+    val = images / step_s
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sample_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_desc(workload_name, cfg, height, width, ctx_len, images, 1),
-                   "note": "reference algorithm (oracle port of f_lite/model.py) on the host CPU; GPUs unused"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config(workload_name, cfg, height, width, ctx_len, images, 1),
+        "note": ("reference arm = the reference's CPU path on this box's host cores; GPUs unused for `value`. "
+                 "`ms_per_step` is the time MEASURED per step (the bounded sample: 2 of the step's blocks); `value` "
+                 "= 1 / ms_per_full_step_extrapolated.  Nothing-extrapolated numbers: `c1_full` (configs[0] in full) "
+                 "and `reference_gpu` (the unmodified module on the B200)."),
+        "ms_per_full_step_extrapolated": step_s * 1e3,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    try:
+        line["c1_full"] = cpu_reference_c1_full()
+    except Exception as e:
+        line["c1_full"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+    if not args.no_reference_gpu and workload_name in ("c1", "c2"):
+        line["reference_gpu"] = reference_gpu_c2(cfg, height, width, ctx_len, images, steps=min(args.steps, 5))
     print(json.dumps(line), flush=True)
-
-
-def workload_desc(name, cfg, height, width, ctx_len, images, n_gpus):
-    L = 16 + (height // 16) * (width // 16)
-    return (f"{name.upper()}: F Lite DiT d{cfg['hidden_size']} depth{cfg['depth']} heads{cfg['num_heads']} "
-            f"{height}x{width}, CFG-batched [neg,pos] => {2 * images} seq x {L} tokens per GPU, ctx {ctx_len}x"
-            f"{cfg['cross_attn_input_size']}, {images} image(s)/GPU x {n_gpus} GPU(s)")
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -215,6 +407,136 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def build_model(cfg, dev, seed=0):
+    import torch
+
+    import flite_b200
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    with torch.device(dev):
+        model = flite_b200.DiT(**cfg)
+    torch.set_default_dtype(prev)
+    random_init_(model, seed=seed)
+    model.eval()
+    model.hoist_context = False          # recompute the (t-independent) context path every step: nothing cached
+    return model
+
+
+def c1_on_gpu(dev):
+    """BASELINE.json configs[0] in full on this GPU: tiny DiT, 256x256, 4 Euler steps, CFG 6, batch 1 (bf16),
+    through flite_b200.denoise (eager and CUDA-graph replay); the like-for-like partner of the reference arm's c1_full."""
+    import torch
+
+    import flite_b200
+    model = build_model(ARCH_TINY, dev)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    lat = torch.randn((1, 16, 32, 32), device=dev, generator=g).bfloat16()
+    pos = torch.randn((1, 256, 4096), device=dev, generator=g).bfloat16()
+    neg = torch.zeros_like(pos)
+    mask = torch.ones((2, 256), device=dev)
+    out = {"config": "C1: tiny DiT d512 depth4 heads2, 256x256, 4 Euler steps, CFG 6, batch 1, bf16, flite_b200.denoise"}
+    for tag, graph in (("eager", False), ("cuda_graph", True)):
+        best = None
+        for rep in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = flite_b200.denoise(model, lat, neg, pos, mask, 4, GUIDANCE, cuda_graph=graph)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 4
+            if rep > 0:
+                best = dt if best is None else min(best, dt)
+        out[f"ms_per_step_{tag}"] = best * 1e3
+        out[f"steps_per_s_{tag}"] = 1.0 / best
+        out["finite"] = bool(torch.isfinite(res.float()).all())
+    out["timing"] = "wall clock around the whole 4-step call incl. launch overhead and (cuda_graph) the capture, best of 3"
+    return out
+
+
+def multi_gpu_layouts(model, dev, world, rank, steps):
+    """The communicating layouts of SURVEY.md 8(e), run with the weights already on the GPUs.  Every rank first runs the
+    1-GPU step itself (reference result + time), then each layout; results are compared on the velocity the step
+    produced (rel-L2, 0.0 = bit-identical)."""
+    import torch
+    import torch.distributed as dist
+
+    import flite_b200
+    from flite_b200 import _lib, ops, parallel
+
+    def rel(a, b):
+        return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    layouts = {2: [("c2", 2, 1), ("c4", 1, 2), ("c4", 2, 1)], 4: [("c4", 1, 4), ("c4", 2, 2)], 8: [("c4", 2, 4)]}.get(world, [])
+    results = []
+    base = {}      # workload -> (1-GPU velocity, 1-GPU ms/step)
+    n = max(2, min(steps, 4))
+    for wl, cfg_ranks, sp_ranks in layouts:
+        arch, height, width, ctx_len, _ = WORKLOADS[wl]
+        g = torch.Generator(device=dev).manual_seed(4321)          # same inputs on every rank
+        lat0 = torch.randn((1, 16, height // 8, width // 8), device=dev, generator=g).bfloat16()
+        pos = torch.randn((1, ctx_len, arch["cross_attn_input_size"]), device=dev, generator=g).bfloat16()
+        neg = torch.zeros_like(pos)
+        ctx2, mask2 = torch.cat([neg, pos]), torch.ones((2, ctx_len), device=dev)
+        t2 = torch.full((2,), 0.9, device=dev).bfloat16()
+        if wl not in base:
+            model.enable_sequence_parallel(None)
+            lat, acc = lat0.clone(), lat0.clone()
+            v1 = flite_b200.denoise_step(model, lat, acc, ctx2, mask2, t2, 0.01, GUIDANCE, True).clone()
+            ms1 = timed(lambda: flite_b200.denoise_step(model, lat, acc, ctx2, mask2, t2, 0.01, GUIDANCE, True), n)
+            base[wl] = (v1, ms1)
+        v1, ms1 = base[wl]
+        sp_group, cfg_group, _, n_rep = parallel.make_groups(cfg_ranks, sp_ranks)
+        model.enable_sequence_parallel(sp_group, fused=sp_group is not None)
+        if cfg_group is not None:
+            half = dist.get_rank(cfg_group)
+            ctx_in, mask_in, t_in = (neg, pos)[half], mask2[:1], t2[:1]
+        else:
+            ctx_in, mask_in, t_in = ctx2, mask2, t2
+        lat, acc = lat0.clone(), lat0.clone()
+        v = flite_b200.denoise_step(model, lat, acc, ctx_in, mask_in, t_in, 0.01, GUIDANCE, True, cfg_group=cfg_group).clone()
+        _lib.watchdog_ok()
+        r = torch.tensor([rel(v, v1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(r, op=dist.ReduceOp.MAX)
+        step = lambda: flite_b200.denoise_step(model, lat, acc, ctx_in, mask_in, t_in, 0.01, GUIDANCE, True, cfg_group=cfg_group)
+        ms = timed(step, n)
+        hs = None
+        if sp_group is not None:      # time spent in the peer-memory flag handshakes of one step (rank-local, max over ranks)
+            ops.TRACE = []
+            step()
+            rep = ops.trace_report()
+            ops.TRACE = None
+            h = torch.tensor([rep.get("p2p signal+wait", (0, 0.0))[1]], device=dev, dtype=torch.float64)
+            dist.all_reduce(h, op=dist.ReduceOp.MAX)
+            hs = float(h.item())
+        _lib.watchdog_ok()
+        model.enable_sequence_parallel(None)
+        name = "x".join(p for p in ((f"cfg{cfg_ranks}" if cfg_ranks > 1 else ""), (f"sp{sp_ranks}" if sp_ranks > 1 else "")) if p)
+        results.append({"workload": workload_desc(wl, arch, height, width, ctx_len, 1, 1).split(",")[0] + f" ({height}x{width}, one image)",
+                        "layout": name, "gpus_per_image": cfg_ranks * sp_ranks, "replicas": n_rep,
+                        "exchange": ("Ulysses: QKV-GEMM / attention epilogues store into the owner rank over NVLink peer memory "
+                                     "(fused, 2 flag handshakes per block)" if sp_ranks > 1 else "") +
+                                    (" + " if sp_ranks > 1 and cfg_ranks > 1 else "") +
+                                    ("CFG halves on different GPUs: one NCCL all-gather of the velocity per step" if cfg_ranks > 1 else ""),
+                        "ms_per_step": ms, "ms_per_step_1gpu": ms1, "speedup_vs_1gpu": ms1 / ms,
+                        "rel_l2_vs_1gpu": float(r.item()), "handshake_ms_per_step": hs, "steps_timed": n})
+    return results
+
+
 def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
     import torch
     import torch.distributed as dist
@@ -232,14 +554,7 @@ def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
     _lib.check(_lib.load().flite_check_device(), "flite_check_device")
 
     # ---- model + synthetic inputs (weights replicated per GPU; each rank denoises its own images)
-    prev = torch.get_default_dtype()
-    torch.set_default_dtype(torch.bfloat16)
-    with torch.device(dev):
-        model = flite_b200.DiT(**cfg)
-    torch.set_default_dtype(prev)
-    random_init_(model, seed=0)
-    model.eval()
-    model.hoist_context = False          # recompute the (t-independent) context path every step: nothing cached
+    model = build_model(cfg, dev)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     b = images
     lat0 = torch.randn((b, 16, height // 8, width // 8), device=dev, generator=g).bfloat16()
@@ -250,7 +565,6 @@ def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
     n_sched = max(30, args.steps + args.warmup)
     sched = flite_b200.pipeline.time_shift_schedule(n_sched, alpha)
     t_all = torch.tensor([[t] * (2 * b) for t, _ in sched], dtype=torch.bfloat16).to(dev)
-    guidance = 6.0
 
     def barrier():
         if world > 1:
@@ -271,7 +585,7 @@ def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
 
     def one_step():
         i = step_i[0] % n_sched
-        flite_b200.denoise_step(model, lat, acc, ctx, mask, t_all[i], sched[i][1], guidance, True)
+        flite_b200.denoise_step(model, lat, acc, ctx, mask, t_all[i], sched[i][1], GUIDANCE, True)
         step_i[0] += 1
 
     for _ in range(args.warmup):
@@ -282,7 +596,7 @@ def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
     dom_events = []
 
     def hook(name, phase, key):
-        if key != dom_key:
+        if key[:4] != dom_key:
             return
         e = torch.cuda.Event(enable_timing=True)
         e.record()
@@ -326,11 +640,13 @@ def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
                 "flops_per_launch": dom_flops, "avg_launch_ms": avg, "launches_timed": len(dom_ms),
                 "share_of_step": avg * len(dom_ms) / args.steps / ms_step, "traffic": None}
         if (M, N, K) == (8224, 24576, 3072):
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
-            # committed as profiles/r1e_ncu_full_top_kernels.csv (518.6 MB + 202.1 MB per launch; the algorithmic
-            # 2(MK + NK + MN/2) = 404 MB: W streams once per 32 MB band of A)
-            roof["traffic"] = 720.6e6
-            roof["traffic_unit"] = "bytes of DRAM traffic per launch (ncu, profiles/r1e_ncu_full_top_kernels.csv)"
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, read from the newest ncu --set full
+            # export under profiles/ (algorithmic: A + W + C = 2(MK + NK + MN/2) bytes)
+            tb, src = ncu_traffic("EPI_SWIGLU")
+            if tb is None:
+                tb, src = ncu_traffic("(flite::GemmEpilogue)2")
+            roof["traffic"] = tb
+            roof["traffic_unit"] = f"bytes of DRAM traffic per launch (ncu --set full, {src})" if src else None
             roof["algorithmic_bytes_per_launch"] = 2.0 * (M * K + N * K + M * N // 2)
 
     # ---- end-to-end run: host (pinned) buffers in, host buffer out, every step
@@ -351,7 +667,7 @@ def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
         mask_d.copy_(mask_h, non_blocking=True)
         t_d.copy_(t_h[i], non_blocking=True)
         acc_d.copy_(lat_d)
-        flite_b200.denoise_step(model, lat_d, acc_d, ctx_d, mask_d, t_d, sched[i][1], guidance, True)
+        flite_b200.denoise_step(model, lat_d, acc_d, ctx_d, mask_d, t_d, sched[i][1], GUIDANCE, True)
         out_h.copy_(lat_d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         lat_h.copy_(out_h)                      # the host owns the state between steps
@@ -372,12 +688,7 @@ def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": workload_desc(workload_name, cfg, height, width, ctx_len, images, world),
-                   "parallelism": f"dp{world} (one image per GPU, no data-path collective)",
-                   "weights": "random-init, de-zeroed (seed 0), replicated per GPU",
-                   "context_kv": "recomputed every step (hoisting disabled)",
-                   "l2": "GBs of weights streamed per step >> 126 MB L2, no flush needed",
-                   "flops_per_step_per_gpu": fl},
+        "config": bench_config(workload_name, cfg, height, width, ctx_len, images, world),
         "tflops_per_gpu": fl / (ms_step * 1e-3) / 1e12,
         "tensor_frac_of_burst_peak": fl / (ms_step * 1e-3) / 1e12 / peaks["bf16"],
         "tensor_frac_of_sustained_peak": fl / (ms_step * 1e-3) / 1e12 / peaks["bf16_sustained"],
@@ -387,8 +698,18 @@ def run_ours(args, cfg, height, width, ctx_len, images, workload_name):
         "gpu_launches": launches, "clocks": clk, "roofline": roof,
     }
     if world == 1 and not args.no_cpu_baseline and args.workload in ("c1", "c2"):
-        steps, cores, sample = cpu_reference_sample(cfg, height, width, ctx_len, images, repeats=1)
-        line["cpu_baseline"] = {"value": 1.0 / steps[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        full, sample, cores, kind, desc = cpu_reference_sample(cfg, height, width, ctx_len, images, repeats=1)
+        line["cpu_baseline"] = {"value": images / full[0], "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+    if world == 1 and not args.no_c1 and args.workload == "c2":
+        try:
+            line["c1"] = c1_on_gpu(dev)
+        except Exception as e:
+            line["c1"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+    if world > 1 and not args.no_multi_gpu and args.workload == "c2":
+        try:
+            line["multi_gpu"] = multi_gpu_layouts(model, dev, world, rank, args.steps)
+        except Exception as e:
+            line["multi_gpu"] = {"failed": f"{type(e).__name__}: {str(e)[:300]}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -403,6 +724,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("FLITE_BENCH_WORKLOAD", "c2"), choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c1", action="store_true")
+    ap.add_argument("--no-multi-gpu", action="store_true", help="N>1: skip the communicating layouts (multi_gpu key)")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="reference arm: skip the GPU run of the unmodified module")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg, height, width, ctx_len, images = WORKLOADS[args.workload]

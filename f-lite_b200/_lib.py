@@ -52,6 +52,7 @@ SIGNATURES = {
     "flite_ipc_close": [_P],
     "flite_p2p_signal": [_P, _I, _I, ctypes.c_uint, _P],
     "flite_p2p_wait": [_P, _I, ctypes.c_uint, _P],
+    "flite_poison_on_abort": [_P, _L, _P],
 }
 
 _lib = None

@@ -412,7 +412,11 @@ __global__ void p2p_signal_kernel(PeerFlagPtrs peers, int n, int my_slot, unsign
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.p[g] + my_slot), "r"(value) : "memory");
     }
 }
-__global__ void p2p_wait_kernel(const unsigned int* flags, int n, unsigned int value) {
+// Cross-RANK wait: the peers are paced by their hosts, so the policy is NCCL's (minutes, configurable through
+// FLITE_TUNE_P2P_TIMEOUT_S), not the 2 s of the intra-kernel barrier watchdog; host-level skew is absorbed before the first
+// peer store by one NCCL all-reduce per forward (model.py), so this spin normally only sees kernel-level skew.  On a
+// time-out the sticky abort word is set and poison_on_abort_kernel turns the forward's output into NaNs (fail closed).
+__global__ void p2p_wait_kernel(const unsigned int* flags, int n, unsigned int value, unsigned long long timeout_ns) {
     const int s = threadIdx.x;
     if (s < n) {
         const uint64_t t0 = globaltimer_ns();
@@ -421,13 +425,22 @@ __global__ void p2p_wait_kernel(const unsigned int* flags, int n, unsigned int v
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + s) : "memory");
             if ((int)(v - value) >= 0) break;
             if (*(volatile unsigned int*)&g_flite_abort != 0) break;
-            if (globaltimer_ns() - t0 > 5000000000ull) {
+            if (globaltimer_ns() - t0 > timeout_ns) {
                 atomicCAS(&g_flite_abort, 0u, (77u << 16) | (unsigned)s | 0x80000000u);
                 break;
             }
         }
     }
     __threadfence_system();
+}
+
+// Fail closed: if any barrier / peer wait of this process has timed out (sticky g_flite_abort), overwrite `buf` with
+// bf16 NaNs so that a caller who never checks flite_watchdog_status cannot consume a half-exchanged result.
+__global__ void poison_on_abort_kernel(uint4* buf, long long n16) {
+    if (*(volatile unsigned int*)&g_flite_abort == 0) return;
+    const uint4 nan4 = make_uint4(0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+        buf[i] = nan4;
 }
 
 // ------------------------------------------------------------------------------------------

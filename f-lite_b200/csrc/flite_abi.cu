@@ -114,14 +114,18 @@ int make_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, u
     return 0;
 }
 
+int cur_dev() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < 64) ? dev : 0;
+}
+
+// per-DEVICE caches (a process may drive more than one GPU): SM count, and "max dynamic smem attribute already set"
 int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return n;
+    static int n[64] = {0};
+    const int dev = cur_dev();
+    if (n[dev] == 0) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    return n[dev];
 }
 
 // Launch attributes of the hot-loop kernels: optional cluster dimension + programmatic dependent launch (PDL).
@@ -147,11 +151,11 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
                 cudaStream_t stream) {
     using S = GemmSmem<kCtaGroup, BLOCK_N, kStages>;
     auto kern = gemm_bf16_kernel<kCtaGroup, BLOCK_N, kStages, kEpi>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};
+    if (!configured[cur_dev()]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kEpi == EPI_QKV_ROPE ? S::TOTAL_QKV : S::TOTAL));
-        configured = true;
+        configured[cur_dev()] = true;
     }
     const int tile_m = 128 * kCtaGroup;
     const int num_tiles = ((p.M + tile_m - 1) / tile_m) * (p.N / BLOCK_N);
@@ -623,7 +627,8 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
     const int64_t q_cols = (int64_t)q_col0 + 256ll * H, k_cols = (int64_t)k_col0 + 256ll * H, v_cols = (int64_t)v_col0 + 256ll * H;
     if (q_cols > ldq || k_cols > ldk || v_cols > ldv)
         return fail(FLITE_ERR_INVALID, "attention: col0 + 256*H exceeds the row stride");
-    static bool configured = false;
+    static bool configured_dev[64] = {false};
+    bool& configured = configured_dev[cur_dev()];
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
@@ -667,7 +672,8 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
     if (variant == FLITE_ATTN_XRES) {
         // persistent cross-attention with resident K/V: every sequence must have <= 256 keys (checked in the kernel)
         if (peers) return fail(FLITE_ERR_INVALID, "attention: the resident-K/V variant has no peer-memory output path");
-        static bool xres_configured = false;
+        static bool xres_configured_dev[64] = {false};
+        bool& xres_configured = xres_configured_dev[cur_dev()];
         if (!xres_configured) {
             CUDA_TRY(cudaFuncSetAttribute(attn_xres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XR_SMEM));
             xres_configured = true;
@@ -815,7 +821,19 @@ int flite_p2p_signal(void* const* peer_flags, int n, int my_slot, unsigned int v
 }
 int flite_p2p_wait(const void* my_flags, int n, unsigned int value, void* stream) {
     if (!my_flags || n <= 0 || n > 8) return fail(FLITE_ERR_INVALID, "p2p_wait: bad arguments");
-    p2p_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned int*)my_flags, n, value);
+    const int secs = g_tuning[FLITE_TUNE_P2P_TIMEOUT_S] > 0 ? g_tuning[FLITE_TUNE_P2P_TIMEOUT_S] : 120;
+    p2p_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned int*)my_flags, n, value,
+                                                        (unsigned long long)secs * 1000000000ull);
+    LAUNCH_CHECK();
+    return 0;
+}
+int flite_poison_on_abort(void* buf, int64_t numel, void* stream) {
+    if (!buf || numel <= 0 || numel % 8 || ((uintptr_t)buf & 15))
+        return fail(FLITE_ERR_INVALID, "poison_on_abort: need a 16-byte aligned bf16 buffer with numel %% 8 == 0");
+    const long long n16 = numel / 8;
+    int blocks = (int)((n16 + 255) / 256);
+    if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+    poison_on_abort_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((uint4*)buf, n16);
     LAUNCH_CHECK();
     return 0;
 }

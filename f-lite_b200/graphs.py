@@ -41,6 +41,9 @@ class GraphedForward:
         torch.cuda.synchronize()
         with torch.cuda.graph(self.graph):
             self.out = self._forward()
+        # the graph has the workspace addresses baked in: keep those allocations alive even if the model later grows
+        # (and thereby replaces) a workspace for a larger shape
+        self._keep = (dict(dit_model._ws), dict(dit_model._rope_cache), dit_model._ctx_cache)
 
     def _forward(self):
         x = torch.cat([self.latents] * 2) if self.dup else self.latents

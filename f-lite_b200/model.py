@@ -251,9 +251,47 @@ class DiT(nn.Module):
             self._rope_cache[key] = (cos[l0:l0 + n].contiguous(), sin[l0:l0 + n].contiguous())
         return self._rope_cache[key]
 
+    @staticmethod
+    def _ver(t):
+        """Cache-key component for a tensor: (address, version counter).  Inference tensors (created under
+        ``torch.inference_mode()``, the usual way to load weights / run the text encoder) have no version counter:
+        their version reads as None, so in-place updates to them are invisible to the caches -- call
+        ``invalidate_caches()`` after such an update (``load_state_dict`` / ``.to()`` do it themselves)."""
+        if t is None:
+            return None
+        return (t.data_ptr(), None if t.is_inference() else t._version, tuple(t.shape), t.dtype)
+
+    def invalidate_caches(self):
+        """Drop every derived tensor (interleaved gate|up weights, concatenated context_kv weights, hoisted context
+        K/V).  Called by ``load_state_dict`` and ``_apply`` (``.to()`` / ``.cuda()`` / ``.bfloat16()``); call it by hand
+        after an in-place weight edit made under ``torch.inference_mode()`` (e.g. a LoRA merge)."""
+        self._gu_cache = {}
+        self._kvcat_cache = None
+        self._ctx_cache = None
+
+    def release_workspaces(self):
+        """Free the activation workspaces, RoPE tables and the sequence-parallel peer buffer (collective over the
+        sequence-parallel group when one is set)."""
+        self._ws = {}
+        self._rope_cache = {}
+        if self._sp_sym is not None:
+            self._sp_sym[1].close()
+            self._sp_sym = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_caches()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_gu_cache"):
+            self.invalidate_caches()
+        return out
+
     def _gate_up(self, i, blk):
         g, u = blk.mlp.gate_proj.weight, blk.mlp.up_proj.weight
-        key = (g.data_ptr(), g._version, u.data_ptr(), u._version)
+        key = (self._ver(g), self._ver(u))
         hit = self._gu_cache.get(i)
         if hit is None or hit[0] != key:
             hit = (key, ops.interleave_gate_up(g.detach(), u.detach()))
@@ -263,7 +301,7 @@ class DiT(nn.Module):
     def _context_kv_cat(self, cross):
         """[K rows of every cross block ; V rows of every cross block] (+ bias), cached until a parameter changes."""
         lins = [self.blocks[i].cross_attn.context_kv for i in cross]
-        key = tuple((l.weight.data_ptr(), l.weight._version, None if l.bias is None else l.bias._version) for l in lins)
+        key = tuple((self._ver(l.weight), self._ver(l.bias)) for l in lins)
         hit = self._kvcat_cache
         if hit is None or hit[0] != key:
             d = self.config.hidden_size
@@ -276,12 +314,16 @@ class DiT(nn.Module):
         return hit[1], hit[2]
 
     def _buf(self, name, shape, device):
-        key = (name, tuple(shape))
-        b = self._ws.get(key)
-        if b is None or b.device != device:
-            b = torch.empty(shape, dtype=torch.bfloat16, device=device)
-            self._ws[key] = b
-        return b
+        """Workspace ``name`` viewed as ``shape``: one flat allocation per name that only ever grows to the largest
+        request (a new batch size / resolution re-uses or replaces it instead of pinning another full set)."""
+        n = 1
+        for s_ in shape:
+            n *= int(s_)
+        flat = self._ws.get(name)
+        if flat is None or flat.device != device or flat.numel() < n:
+            flat = torch.empty(max(n, 1), dtype=torch.bfloat16, device=device)
+            self._ws[name] = flat
+        return flat[:n].view(shape)
 
     # ------------------------------------------------------------------ context (t-independent, K13)
     def prepare_context(self, context: torch.Tensor, mask: Optional[torch.Tensor]):
@@ -314,11 +356,14 @@ class DiT(nn.Module):
         return SimpleNamespace(kvs=kvs, cu_k=cu_k, B=B, Lc=Lc)
 
     def _context(self, context, mask):
-        if not self.hoist_context:
+        # inference tensors carry no version counter, so an in-place change of the embeddings could not be seen: do not
+        # hoist for them (0.25 % of a step's FLOPs); callers that want the hoist anyway use prepare_context() themselves
+        if not self.hoist_context or context.is_inference() or (mask is not None and mask.is_inference()):
             return self.prepare_context(context, mask)
-        key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype,
-               None if mask is None else (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype),
-               tuple((p.data_ptr(), p._version) for p in (self.context_proj.weight, self.context_norm.weight)))
+        cross = [b.cross_attn.context_kv for b in self.blocks if b.cross_attn is not None]
+        key = (self._ver(context), self._ver(mask),
+               tuple(self._ver(p) for p in (self.context_proj.weight, self.context_proj.bias, self.context_norm.weight)),
+               tuple((self._ver(l.weight), self._ver(l.bias)) for l in cross))
         if self._ctx_cache is None or self._ctx_cache[0] != key:
             # keep references to the keyed tensors so their storage cannot be recycled under the cache
             self._ctx_cache = (key, self.prepare_context(context, mask), context, mask)
@@ -408,6 +453,14 @@ class DiT(nn.Module):
         if sp is not None and self.sp_fused:
             sym, p2p_recv, p2p_ao, recv_tab, ao_tab = self._sym(B, L, Lq, dq, d, dev)
             stream = torch.cuda.current_stream().cuda_stream
+            # Host-paced skew between the ranks (one of them saving an image, a GC pause, first-call lazy loading) is
+            # absorbed HERE by NCCL, which tolerates minutes: one 4-byte all-reduce orders the ranks' streams before the
+            # first peer store of this forward, so the device-side flag spins below only ever cover kernel-level skew.
+            tok = self._ws.get("sp_token")
+            if tok is None or tok.device != dev:
+                tok = torch.zeros(1, dtype=torch.int32, device=dev)
+                self._ws["sp_token"] = tok
+            dist.all_reduce(tok, group=sp)
         elif sp is not None:
             a2a_send = self._buf("a2a_send", (B, P * Lq, 3 * dq), dev)   # [sample][dest rank][local token][q|k|v]
             a2a_recv = self._buf("a2a_recv", (B, L, 3 * dq), dev)        # [sample][full sequence][q|k|v of my heads]
@@ -482,4 +535,8 @@ class DiT(nn.Module):
             dist.all_gather_into_tensor(gathered.view(P * B * Lq, no), o, group=sp)
             o = ops.permute_021(gathered).view(B * L, no)
         out = ops.unpatchify(o, B, C, H, W, p, N_REGISTER)
+        if sp is not None and self.sp_fused:
+            # fail closed: a timed-out peer wait leaves a half-exchanged buffer behind; callers of forward() that never
+            # look at flite_watchdog_status (denoise() does, once per trajectory) must not get plausible numbers from it
+            ops.poison_on_abort(out)
         return out if x.dtype == torch.bfloat16 else out.to(x.dtype)

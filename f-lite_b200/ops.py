@@ -420,6 +420,16 @@ def permute_021(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.
     return out
 
 
+def poison_on_abort(buf: torch.Tensor) -> None:
+    """Stream-ordered fail-closed guard: NaN-fill ``buf`` if a kernel-side wait of this process has timed out."""
+    lib = _lib.load()
+    _chk(buf, "buf")
+    if not buf.is_contiguous():
+        raise _lib.FliteError("poison_on_abort: buffer must be contiguous")
+    _lib.check(lib.flite_poison_on_abort(buf.data_ptr(), buf.numel(), _stream()), "poison_on_abort")
+    LAUNCHES[0] += 1
+
+
 def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
     """[inter, d] x2 -> [2*inter, d] with rows interleaved in groups of 64 ([g 64 | u 64] per 128 rows) so that
     one accumulator tile holds matching gate / up columns for the EPI_SWIGLU epilogue."""

@@ -7,7 +7,8 @@ The reference has no multi-GPU inference at all; what exists her
   gather of the finished latents.
 * **Ulysses sequence parallel** (config C4, single 2048^2 image): tokens are sharded L/P per rank everywhere except
   self-attention, which is head-sharded over the full sequence; two all-to-alls per block over NCCL/NVLink
-  (see ``ulysses.py``).
+  (``DiT.enable_sequence_parallel`` in ``model.py``; the fused peer-memory exchange lives in ``peer.py`` and the
+  ``flite_gemm_qkv_p2p`` / ``flite_attention_varlen_p2p`` kernels).
 """
 from __future__ import annotations
 
@@ -47,6 +48,13 @@ def dp_denoise(denoise_fn: Callable, latents: torch.Tensor, negative_embeds: tor
         local = latents[:0]
     if not gather:
         return local
+    # a rank with an empty shard does not know the dtype denoise_fn returns on the others (bf16 latents or the fp32
+    # accumulator): agree on it first (max over ranks of a dtype code, 0 = "no result here")
+    codes = [None, torch.bfloat16, torch.float16, torch.float32, torch.float64]
+    code = torch.tensor([codes.index(local.dtype) if (hi > lo and local.dtype in codes) else 0], device=latents.device)
+    dist.all_reduce(code, op=dist.ReduceOp.MAX, group=group)
+    if int(code.item()) > 0:
+        local = local.to(codes[int(code.item())])
     # ragged all-gather: pad every shard to the largest one
     cap = (B + world - 1) // world
     pad = torch.zeros((cap,) + tuple(latents.shape[1:]), dtype=local.dtype, device=local.device)

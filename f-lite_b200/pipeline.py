@@ -216,9 +216,10 @@ class FLitePipeline:
                     {"role": "user", "content": [{"type": "text", "text": caption}]}]
         return self.processor.apply_chat_template(messages, tokenize=False, add_generation_prompt=True)
 
-    def encode_prompt(self, prompt, negative_prompt=None, device=None, dtype=None, max_sequence_length=512,
-                      return_index=-8):
-        """pipeline.py:126-175; additionally returns the attention mask the 4-argument DiT needs."""
+    def encode_prompt_with_masks(self, prompt, negative_prompt=None, device=None, dtype=None, max_sequence_length=512,
+                                 return_index=-8):
+        """pipeline.py:126-175 plus the attention masks the 4-argument DiT forward needs (model.py:526): returns
+        ``(prompt_embeds, negative_embeds, prompt_mask, negative_mask)``."""
         if self.text_encoder is None:
             raise RuntimeError("no text_encoder: pass prompt_embeds= / negative_embeds= to __call__")
         if isinstance(prompt, str):
@@ -236,9 +237,16 @@ class FLitePipeline:
         else:
             if isinstance(negative_prompt, str):
                 negative_prompt = [negative_prompt]
-            neg, _, neg_mask, _ = self.encode_prompt(negative_prompt, device=device, dtype=dtype,
-                                                     return_index=return_index)
+            neg, _, neg_mask, _ = self.encode_prompt_with_masks(negative_prompt, device=device, dtype=dtype,
+                                                                return_index=return_index)
         return embeds, neg, mask, neg_mask
+
+    def encode_prompt(self, prompt, negative_prompt=None, device=None, dtype=None, max_sequence_length=512,
+                      return_index=-8):
+        """Same contract as the reference (pipeline.py:126-175): returns ``(prompt_embeds, negative_embeds)``."""
+        embeds, neg, _, _ = self.encode_prompt_with_masks(prompt, negative_prompt, device, dtype, max_sequence_length,
+                                                          return_index)
+        return embeds, neg
 
     @torch.no_grad()
     def __call__(
@@ -270,7 +278,7 @@ class FLitePipeline:
         acc_dtype = kwargs.pop("acc_dtype", dtype)
         cuda_graph = kwargs.pop("cuda_graph", False)       # replay the DiT forward from a CUDA graph (launch-bound shapes)
         if prompt_embeds is None:
-            prompt_embeds, negative_embeds, prompt_mask, negative_mask = self.encode_prompt(
+            prompt_embeds, negative_embeds, prompt_mask, negative_mask = self.encode_prompt_with_masks(
                 prompt, negative_prompt, device=device, dtype=dtype, return_index=self.return_index)
         if negative_embeds is None:
             negative_embeds = torch.zeros_like(prompt_embeds)                      # pipeline.py:160-161

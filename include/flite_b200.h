@@ -71,6 +71,7 @@ extern "C" {
 #define FLITE_TUNE_GEMM_HINT_B 10     /* same for the W-tile loads */
 #define FLITE_TUNE_PATCH_EMBED 11     /* 0 auto: patchify = gather + tcgen05 GEMM when C*P*P % 64 == 0 | 1 CUDA-core patch_embed kernel */
 #define FLITE_TUNE_ATTN_VARIANT_SHORT_K 12 /* attention variant for FLITE_ATTN_AUTO calls with <= 512 keys per sequence on average (cross-attention); 0 = same as the long-key default; 9 (FLITE_ATTN_XRES) = the host model requests the resident-K/V kernel when the padded context has <= 256 tokens (opt-in) */
+#define FLITE_TUNE_P2P_TIMEOUT_S 13    /* seconds a cross-rank flag wait (flite_p2p_wait) may spin before it aborts; 0 = default 120 */
 #define FLITE_TUNE_GEMM_BAND 5       /* 0 = L2-aware band rasterisation for large M (default), 1 = single band */
 int flite_set_tuning(int key, int value);
 int flite_get_tuning(int key);   /* current value of a knob (0 for an unknown key) */
@@ -198,7 +199,11 @@ int flite_attention_varlen_p2p(const void* q, int64_t ldq, int64_t rows_q, int q
 
 /* Symmetric peer allocations (cudaMalloc + CUDA IPC) and stream-ordered cross-GPU completion flags.
  *   signal: after all prior work of `stream`, write `value` into slot my_slot of each peer's flag array (uint32[8]);
- *   wait:   block `stream` until slots [0, n) of the local flag array are >= value (monotonic epochs; 5 s watchdog). */
+ *   wait:   block `stream` until slots [0, n) of the local flag array are >= value (monotonic epochs).  The peers are
+ *           paced by their hosts, so the wait tolerates FLITE_TUNE_P2P_TIMEOUT_S seconds (default 120) before it sets
+ *           the sticky watchdog word; flite_poison_on_abort then fails the result closed.
+ *   poison_on_abort: stream-ordered, no host sync: if the watchdog word of this process is set, overwrite the bf16
+ *           buffer with NaNs (called on the output of every sequence-parallel forward). */
 int flite_p2p_alloc(int64_t bytes, void** out);
 int flite_p2p_free(void* p);
 int flite_ipc_get_handle(const void* p, void* handle64);
@@ -206,6 +211,7 @@ int flite_ipc_open(const void* handle64, void** out);
 int flite_ipc_close(void* p);
 int flite_p2p_signal(void* const* peer_flags, int n, int my_slot, unsigned int value, void* stream);
 int flite_p2p_wait(const void* my_flags, int n, unsigned int value, void* stream);
+int flite_poison_on_abort(void* buf, int64_t numel, void* stream);
 
 #ifdef __cplusplus
 }

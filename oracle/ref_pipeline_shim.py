@@ -24,7 +24,9 @@ from torch import nn
 from . import ref_shim
 from .vae_decoder import SCALING_FACTOR as TOY_SCALING, SHIFT_FACTOR as TOY_SHIFT, toy_decode
 
-REF_PIPELINE = "/root/reference/f_lite/pipeline.py"
+from .build_ref import ref_path
+
+REF_PIPELINE = ref_path("f_lite/pipeline.py")
 
 
 def _install_stubs():

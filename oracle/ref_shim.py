@@ -1,11 +1,16 @@
-"""TEST INFRASTRUCTURE, BUILD CONTAINER ONLY -- import the UNMODIFIED reference DiT.
+"""TEST INFRASTRUCTURE -- import the UNMODIFIED reference DiT.
 
-``/root/reference/f_lite/model.py`` imports diffusers / peft / liger_kernel /
-flash_attn_interface, none of which are usable on CPU in this image.  This module registers
-minimal stub modules for exactly those import names and loads the reference file by path, so
-that ``oracle/make_golden.py`` can run the *real* module and pin the restatement in
-``oracle/dit_oracle.py`` against it.  ``/root/reference`` does not exist on the GPU box, so
-nothing imported at GPU-test / bench / smoke time may import this file.
+``f_lite/model.py`` imports diffusers / peft (not installed), liger_kernel (Triton: GPU only) and
+flash_attn_interface (FlashAttention-3: not installed, Hopper-only).  This module registers minimal stub modules for
+exactly those import names and loads the reference file by path -- from ``/root/reference`` in the build container,
+from the travelled copy ``oracle/_ref/f_lite/model.py`` on the GPU box (``oracle/build_ref.py``).  Two backends:
+
+* ``backend="cpu"``: LigerRMSNorm / LigerSwiGLUMLP / flash_attn_varlen_func are the torch restatements of
+  ``oracle/dit_oracle.py`` -- what ``oracle/make_golden.py`` uses to pin the restatement of everything else.
+* ``backend="gpu"``: the REAL ``liger_kernel.transformers`` modules (0.8.0, Triton) and the REAL FlashAttention-2
+  ``flash_attn.flash_attn_varlen_func`` (2.8.3; same call signature, returns ``out`` where FA3 returns ``(out, lse)``)
+  behind the ``flash_attn_interface`` name -- "the reference bf16 path" of BASELINE.json on a B200.  Used by
+  ``tests/test_reference_gpu.py`` and ``bench.py --impl reference``; never by the product.
 """
 from __future__ import annotations
 
@@ -17,10 +22,18 @@ import types
 import torch
 from torch import nn
 
-REF_MODEL = "/root/reference/f_lite/model.py"
+from .build_ref import ref_path
 
 
-def _install_stubs():
+def ref_model_path() -> str:
+    p = ref_path("f_lite/model.py")
+    if p is None:
+        raise FileNotFoundError("reference model.py not found: neither /root/reference nor oracle/_ref "
+                                "(run `python -m oracle.build_ref` in the build container)")
+    return p
+
+
+def _install_stubs(backend: str = "cpu"):
     from . import dit_oracle as O
 
     def mod(name):
@@ -67,6 +80,18 @@ def _install_stubs():
     mod("peft").get_peft_model_state_dict = lambda *a, **k: {}
     mod("peft").set_peft_model_state_dict = lambda *a, **k: None
 
+    if backend == "gpu":
+        # the real third-party kernels: liger_kernel (Triton) as is, FA2 behind FA3's module name
+        import flash_attn
+        import liger_kernel.transformers  # noqa: F401  (model.py imports the real classes from it)
+
+        def fa2_varlen(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, softmax_scale):
+            return flash_attn.flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                                                     softmax_scale=softmax_scale, causal=False), None
+
+        mod("flash_attn_interface").flash_attn_varlen_func = fa2_varlen
+        return
+
     class LigerRMSNorm(nn.Module):
         def __init__(self, hidden_size, eps=1e-6):
             super().__init__()
@@ -98,24 +123,35 @@ def _install_stubs():
     mod("flash_attn_interface").flash_attn_varlen_func = flash_attn_varlen_func
 
 
-def load_reference_model_module():
-    saved = {k: sys.modules.get(k) for k in ("liger_kernel", "liger_kernel.transformers")}
-    _install_stubs()
-    spec = importlib.util.spec_from_file_location("_flite_ref_model", REF_MODEL)
+def load_reference_model_module(backend: str = "cpu"):
+    names = ("liger_kernel", "liger_kernel.transformers", "flash_attn_interface")
+    saved = {k: sys.modules.get(k) for k in names}
+    if backend == "cpu":             # a real liger_kernel imported earlier must not shadow the CPU stubs
+        for k in names:
+            sys.modules.pop(k, None)
+    _install_stubs(backend)
+    spec = importlib.util.spec_from_file_location(f"_flite_ref_model_{backend}", ref_model_path())
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
-    for k, v in saved.items():       # do not leave a stubbed liger_kernel behind
-        if v is None:
-            sys.modules.pop(k, None)
-        else:
-            sys.modules[k] = v
+    if backend == "cpu":
+        for k, v in saved.items():   # do not leave a stubbed liger_kernel behind
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
     return m
 
 
-def build_reference_dit(cfg: dict, sd: dict, dtype=torch.float32):
+def build_reference_dit(cfg: dict, sd: dict, dtype=torch.float32, backend: str = "cpu", device=None):
     """Instantiate the reference DiT, load ``sd`` (reference keys) and cast like users do."""
-    m = load_reference_model_module()
-    model = m.DiT(**cfg)
-    missing, unexpected = model.load_state_dict(sd, strict=True)
-    assert not missing and not unexpected
-    return model.to(dtype).eval()
+    m = load_reference_model_module(backend)
+    if device is not None:
+        with torch.device(device):   # fp32 construction on the device, then the user's .to(dtype) (RoPE buffers included)
+            model = m.DiT(**cfg)
+    else:
+        model = m.DiT(**cfg)
+    if sd is not None:
+        missing, unexpected = model.load_state_dict(sd, strict=True)
+        assert not missing and not unexpected
+    model = model.to(dtype).eval()
+    return model.to(device) if device is not None else model

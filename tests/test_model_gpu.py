@@ -82,6 +82,35 @@ def test_context_cache_is_invalidated_by_in_place_updates(golden_dir):
     assert not torch.equal(a, b) and torch.equal(b, c)
 
 
+def test_inference_mode_tensors_and_in_place_weight_edits(golden_dir):
+    """Weights / embeddings created under torch.inference_mode() have no version counter: the forward must
+    run, must not serve a stale hoisted context for them, and invalidate_caches() must pick up an in-place weight edit."""
+    from oracle.make_golden import build_case
+    g = torch.load(os.path.join(golden_dir, "tiny_256.pt"), weights_only=False)
+    sd, x, ctx, mask, t = build_case(g["recipe"], device=DEV)
+    ref = _model(g["recipe"]["cfg"], sd)(x.bfloat16(), ctx.bfloat16(), mask.bfloat16(), t.bfloat16())
+    with torch.inference_mode():
+        m = _model(g["recipe"]["cfg"], {k: v.clone() for k, v in sd.items()})
+        cb = ctx.bfloat16()
+        a = m(x.bfloat16(), cb, mask.bfloat16(), t.bfloat16())
+        assert torch.equal(a, ref)
+        cb.mul_(0.5)                                              # same storage, no version counter to notice it
+        b = m(x.bfloat16(), cb, mask.bfloat16(), t.bfloat16())
+        assert not torch.equal(a, b)
+        m.blocks[0].mlp.gate_proj.weight.mul_(0.5)                # e.g. a LoRA merge under inference mode
+        m.blocks[0].cross_attn.context_kv.bias.add_(0.25)
+        m.invalidate_caches()
+        c = m(x.bfloat16(), cb, mask.bfloat16(), t.bfloat16())
+        assert not torch.equal(b, c)
+    m2 = _model(g["recipe"]["cfg"], sd)                           # normal tensors: version counters catch the edit
+    b2 = m2(x.bfloat16(), cb.clone(), mask.bfloat16(), t.bfloat16())
+    assert torch.equal(b2, b)
+    with torch.no_grad():
+        m2.blocks[0].mlp.gate_proj.weight.mul_(0.5)
+        m2.blocks[0].cross_attn.context_kv.bias.add_(0.25)
+    assert torch.equal(m2(x.bfloat16(), cb.clone(), mask.bfloat16(), t.bfloat16()), c)
+
+
 def test_sampler_trajectory_vs_reference(golden_dir):
     """Config C1 of BASELINE.json: tiny DiT, 256x256, 4 Euler steps, CFG 6, batch 1."""
     import flite_b200
