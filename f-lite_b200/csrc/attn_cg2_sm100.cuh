@@ -30,6 +30,10 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if ((qt & ~1) * 128 >= q_len) return;  // uniform for the whole cluster, before any barrier / TMEM allocation
     const int k_beg = p.cu_k[b], k_len = p.cu_k[b + 1] - k_beg;
     const int n_tiles = (k_len + 127) / 128;
+    // Ragged last key tile (4112 = 32*128 + 16 at C2): its MMAs only cover the valid keys rounded up to 16 -- S = Q K^T
+    // with N = tail_n instead of 128 (each CTA then stages keys [rank*tail_n/2, +tail_n/2) of the tile) and O += P V over
+    // tail_n/16 K-steps instead of 8.  The softmax masks columns >= the valid count as before.
+    const int tail_n = (k_len > 0 && (k_len & 127)) ? (((k_len & 127) + 15) & ~15) : 128;
     const uint32_t cta_rank = cluster_ctarank();
     const bool is_leader = cta_rank == 0;
 
@@ -98,9 +102,10 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 mbar_wait<true>(&k_empty[st], ph, 21);
                 if (is_leader) mbar_arrive_expect_tx(&k_full[st], 2 * 32768);
 #pragma unroll
+                const int kn_half = (j == n_tiles - 1 ? tail_n : 128) >> 1;   // keys of this tile staged per CTA
                 for (int c = 0; c < 4; ++c)   // this CTA's 64 key rows, 4 chunks of 64 head-dim columns
                     tma_load_2d_cg2(smem + ATT2_SK + st * 32768 + c * 8192, &tmap_k, &k_full[st], 0,
-                                    p.k_col0 + h * 256 + c * 64, krow + (int)cta_rank * 64);
+                                    p.k_col0 + h * 256 + c * 64, krow + (int)cta_rank * kn_half);
                 mbar_wait<true>(&v_empty[st], ph, 22);
                 if (is_leader) mbar_arrive_expect_tx(&v_full[st], 2 * 32768);
 #pragma unroll
@@ -113,7 +118,8 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     } else if (warp_idx == 1) {
         // ================================ MMA issuer (leader CTA) ================================
         if (is_leader && elect_one() && n_tiles > 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(256, 128, 0, 0);   // Q (K-major) x K (K-major)
+            constexpr uint32_t idesc_s_full = make_idesc_bf16(256, 128, 0, 0);   // Q (K-major) x K (K-major)
+            const uint32_t idesc_s_tail = make_idesc_bf16(256, tail_n, 0, 0);
             constexpr uint32_t idesc_o = make_idesc_bf16(256, 256, 0, 1);   // P (K-major) x V (MN-major)
             const uint32_t sq = smem_u32(smem + ATT2_SQ), sk = smem_u32(smem + ATT2_SK);
             const uint32_t sv = smem_u32(smem + ATT2_SV), sp = smem_u32(smem + ATT2_SP);
@@ -122,6 +128,7 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 if (!((p.debug & 2) && j >= 2)) mbar_wait<true>(&k_full[st], (j >> 1) & 1, 23);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (j & 1) * 128;
+                const uint32_t idesc_s = (j == n_tiles - 1) ? idesc_s_tail : idesc_s_full;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const uint32_t offq = (k >> 2) * 16384 + (k & 3) * 32;
@@ -140,8 +147,10 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 mbar_wait<true>(p_full, j & 1, 25);
                 if (!((p.debug & 2) && j >= 2)) mbar_wait<true>(&v_full[st], (j >> 1) & 1, 26);
                 tc_fence_after();
+                const int pv_steps = (j == n_tiles - 1) ? (tail_n >> 4) : 8;   // 16 keys per K-step
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
+                    if (k >= pv_steps) break;
                     const uint64_t db = make_smem_desc_sw128(sv + st * 32768 + k * 2048, 16384, 1024);
                     if constexpr (kPTmem) {
                         // A = P_j: rows = lanes, 16 keys = 8 packed columns per K-step, inside S_j's columns

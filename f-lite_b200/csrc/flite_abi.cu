@@ -23,7 +23,7 @@ using namespace flite;
 namespace {
 
 thread_local char g_err[512] = "";
-int g_tuning[16] = {0};   // FLITE_TUNE_* knobs (A/B switches for benchmarking)
+int g_tuning[32] = {0};   // FLITE_TUNE_* knobs (A/B switches for benchmarking)
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -147,8 +147,8 @@ int fill_launch_attrs(cudaLaunchAttribute* attr, int cluster_x) {
 }
 
 template <int kCtaGroup, int BLOCK_N, int kStages, int kEpi>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, GemmParams p,
-                cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& tah,
+                GemmParams p, cudaStream_t stream) {
     using S = GemmSmem<kCtaGroup, BLOCK_N, kStages>;
     auto kern = gemm_bf16_kernel<kCtaGroup, BLOCK_N, kStages, kEpi>;
     static bool configured[64] = {false};
@@ -183,9 +183,14 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         else if (g_tuning[FLITE_TUNE_GEMM_BAND] > 1) g = g_tuning[FLITE_TUNE_GEMM_BAND];   // explicit band height (tuning)
         else if (w_bytes <= (96ll << 20)) g = 2;
         else {
-            g = (32ll << 20) / a_tile_bytes;
-            if (g < 1) g = 1;
-            if (g > 16) g = 16;
+            // a band of A of <= ~32 MB stays L2-resident while W streams past it once per band; the bands are BALANCED
+            // (33 M-tiles -> 17 + 16, not 16 + 16 + 1: a one-tile last band re-streams the whole of W from DRAM for 3 %
+            // of the work -- r1f ncu: 518 MB read per gate|up launch for 201 MB of operands)
+            long long g_max = (32ll << 20) / a_tile_bytes;
+            if (g_max < 1) g_max = 1;
+            if (g_max > 24) g_max = 24;
+            const long long n_bands = (num_m_tiles + g_max - 1) / g_max;
+            g = (num_m_tiles + n_bands - 1) / n_bands;
         }
         if (g > num_m_tiles) g = num_m_tiles;
         p.band_m = (int)g;
@@ -195,6 +200,13 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         };
         p.hint_a = policy(g_tuning[FLITE_TUNE_GEMM_HINT_A]);
         p.hint_b = policy(g_tuning[FLITE_TUNE_GEMM_HINT_B]);
+        // narrow last M-tile (<= 128 valid rows of the 256): M = 128 MMAs, half the padding cost.  Not for the QKV epilogue
+        // (needs a whole head per thread pair), and only when the first band (which holds the narrow tile) is made of
+        // whole-width units.
+        const int tail_rows = p.M % tile_m;
+        p.narrow_m = (kCtaGroup == 2 && kEpi != EPI_QKV_ROPE && tail_rows > 0 && tail_rows <= tile_m / 2 &&
+                      num_m_tiles >= 2 && g_tuning[FLITE_TUNE_GEMM_NARROW_M] == 0 &&
+                      p.full_units >= (int)g * (p.N / BLOCK_N)) ? 1 : 0;
     }
     int clusters = max_clusters;
     if (clusters > p.num_units) clusters = p.num_units;
@@ -206,21 +218,21 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
     cfg.numAttrs = fill_launch_attrs(attr, kCtaGroup);
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbh, p));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tbh, tah, p));
     return 0;
 }
 
 template <int kCtaGroup, int BLOCK_N, int kStages>
-int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const GemmParams& p,
-                 cudaStream_t s) {
+int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const CUtensorMap& tah,
+                 const GemmParams& p, cudaStream_t s) {
     switch (epi) {
-        case EPI_STORE: return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_STORE>(ta, tb, tbh, p, s);
-        case EPI_GATED_RES: return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_GATED_RES>(ta, tb, tbh, p, s);
+        case EPI_STORE: return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_STORE>(ta, tb, tbh, tah, p, s);
+        case EPI_GATED_RES: return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_GATED_RES>(ta, tb, tbh, tah, p, s);
         case EPI_SWIGLU:
-            if constexpr (BLOCK_N % 128 == 0) return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_SWIGLU>(ta, tb, tbh, p, s);
+            if constexpr (BLOCK_N % 128 == 0) return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_SWIGLU>(ta, tb, tbh, tah, p, s);
             break;
         case EPI_QKV_ROPE:
-            if constexpr (BLOCK_N == 256) return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_QKV_ROPE>(ta, tb, tbh, p, s);
+            if constexpr (BLOCK_N == 256) return launch_gemm<kCtaGroup, BLOCK_N, kStages, EPI_QKV_ROPE>(ta, tb, tbh, tah, p, s);
             break;
     }
     return fail(FLITE_ERR_INVALID, "epilogue %d not available for N-tile %d", epi, BLOCK_N);
@@ -234,12 +246,12 @@ int flite_abi_version(void) { return FLITE_ABI_VERSION; }
 const char* flite_last_error(void) { return g_err; }
 
 int flite_set_tuning(int key, int value) {
-    if (key < 0 || key >= 16) return fail(FLITE_ERR_INVALID, "set_tuning: unknown key %d", key);
+    if (key < 0 || key >= 32) return fail(FLITE_ERR_INVALID, "set_tuning: unknown key %d", key);
     g_tuning[key] = value;
     return 0;
 }
 
-int flite_get_tuning(int key) { return (key >= 0 && key < 16) ? g_tuning[key] : 0; }
+int flite_get_tuning(int key) { return (key >= 0 && key < 32) ? g_tuning[key] : 0; }
 
 int flite_check_device(void) {
     int dev = 0;
@@ -568,8 +580,10 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     }
     p.stage_stores = (epilogue == EPI_QKV_ROPE && (peers != nullptr || g_tuning[FLITE_TUNE_QKV_STAGED_STORES])) ? 1 : 0;
 
-    CUtensorMap ta, tb, tbh;
+    CUtensorMap ta, tb, tbh, tah;
     int rc = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128);
+    if (rc) return rc;
+    rc = make_tmap(&tah, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64);     // 64-row boxes of the narrow last M-tile
     if (rc) return rc;
     rc = make_tmap(&tb, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(block_n / cg));
     if (rc) return rc;
@@ -577,10 +591,10 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     switch (variant) {
-        case FLITE_GEMM_1CTA_N256: return dispatch_epi<1, 256, 4>(epilogue, ta, tb, tbh, p, s);
-        case FLITE_GEMM_2CTA_N256: return dispatch_epi<2, 256, 6>(epilogue, ta, tb, tbh, p, s);
-        case FLITE_GEMM_1CTA_N128: return dispatch_epi<1, 128, 6>(epilogue, ta, tb, tbh, p, s);
-        case FLITE_GEMM_1CTA_N64: return dispatch_epi<1, 64, 8>(epilogue, ta, tb, tbh, p, s);
+        case FLITE_GEMM_1CTA_N256: return dispatch_epi<1, 256, 4>(epilogue, ta, tb, tbh, tah, p, s);
+        case FLITE_GEMM_2CTA_N256: return dispatch_epi<2, 256, 6>(epilogue, ta, tb, tbh, tah, p, s);
+        case FLITE_GEMM_1CTA_N128: return dispatch_epi<1, 128, 6>(epilogue, ta, tb, tbh, tah, p, s);
+        case FLITE_GEMM_1CTA_N64: return dispatch_epi<1, 64, 8>(epilogue, ta, tb, tbh, tah, p, s);
     }
     return fail(FLITE_ERR_INVALID, "gemm: unreachable");
 }

@@ -59,6 +59,13 @@ struct GemmParams {
     // Rasterisation: tiles are ordered band by band (band_m consecutive M-tiles), N-tile by N-tile inside a band and
     // M fastest, so that a band of A (band_m x TILE_M x K) stays L2-resident while W streams past it once per band.
     int band_m;
+    // Ragged M (8224 = 32*256 + 32 at C2): when the last 256-row M-tile holds <= 128 valid rows it is run as a NARROW tile,
+    // tcgen05.mma cta_group::2 with M = 128 (64 rows per CTA) -- measured 64 instead of 128 cycles per K-step
+    // (tools/probe_umma.cu), i.e. the padding costs half.  narrow_m = 1 enables it; the narrow tile is logical M-block 0
+    // of the rasterisation (so it never lands in the half-width tail units).  TMEM layout of that mode ("layout B"):
+    // lanes 0-63 = rows 0-63 x accumulator columns [0, N/2), lanes 64-127 = the same rows x columns [N/2, N), both at
+    // TMEM columns [0, N/2).
+    int narrow_m;
     // L2 eviction-priority hints of the A / W tile loads (0 = plain load); chosen with the band height so that the operand
     // the rasterisation keeps resident is evict_last and the one that streams past it is evict_first.
     unsigned long long hint_a, hint_b;
@@ -90,7 +97,8 @@ struct GemmSmem {
 template <int kCtaGroup, int BLOCK_N, int kStages, int kEpi>
 __global__ void __launch_bounds__(gemm_threads(kEpi), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_b_half, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_b_half, const __grid_constant__ CUtensorMap tmap_a_half,
+                 const GemmParams p) {
     using S = GemmSmem<kCtaGroup, BLOCK_N, kStages>;
     constexpr int TILE_M = 128 * kCtaGroup;
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
@@ -155,7 +163,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int gm = min(p.band_m, num_m_tiles - m_first);
         m_blk = m_first + rem % gm;
         n_blk = rem / gm;
+        if (p.narrow_m) m_blk = (m_blk == 0) ? num_m_tiles - 1 : m_blk - 1;   // logical block 0 = the narrow (last) M-tile
     };
+    auto is_narrow = [&](int m_blk) { return kCtaGroup == 2 && p.narrow_m && m_blk == num_m_tiles - 1; };
     // unit -> (tile, half): half == -1 means the whole tile, 0/1 the left/right BLOCK_N/2 columns
     auto unit_tile = [&](int u, int& tile, int& half) {
         if (u < p.full_units) { tile = u; half = -1; }
@@ -176,24 +186,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int bn_cta = (half < 0) ? S::BN_CTA : S::BN_CTA / 2;       // W rows this CTA stages
                 int m_blk, n_blk;
                 tile_coords(tile, m_blk, n_blk);
-                const int m0 = m_blk * TILE_M + (int)cta_rank * 128;
+                const bool narrow = is_narrow(m_blk);
+                const int m0 = m_blk * TILE_M + (int)cta_rank * (narrow ? 64 : 128);
                 const int n0 = n_blk * BLOCK_N + (half > 0 ? BLOCK_N / 2 : 0) + (int)cta_rank * bn_cta;
                 const CUtensorMap* tb = (half < 0) ? &tmap_b : &tmap_b_half;
-                const uint32_t stage_bytes = S::A_BYTES + bn_cta * GEMM_BLOCK_K * 2;
+                const CUtensorMap* ta = narrow ? &tmap_a_half : &tmap_a;
+                const uint32_t stage_bytes = (narrow ? S::A_BYTES / 2 : S::A_BYTES) + bn_cta * GEMM_BLOCK_K * 2;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait<kCtaGroup == 2>(&empty_bar[stage], phase ^ 1, 1);
                     uint8_t* sa = smem + stage * S::STAGE_BYTES;
                     uint8_t* sb = sa + S::A_BYTES;
                     if constexpr (kCtaGroup == 1) {
                         mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-                        if (p.hint_a) tma_load_2d_hint(sa, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0, p.hint_a);
-                        else tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+                        if (p.hint_a) tma_load_2d_hint(sa, ta, &full_bar[stage], kb * GEMM_BLOCK_K, m0, p.hint_a);
+                        else tma_load_2d(sa, ta, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
                         if (p.hint_b) tma_load_2d_hint(sb, tb, &full_bar[stage], kb * GEMM_BLOCK_K, n0, p.hint_b);
                         else tma_load_2d(sb, tb, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
                     } else {
                         if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
-                        if (p.hint_a) tma_load_2d_cg2_hint(sa, &tmap_a, &full_bar[stage], 0, kb * GEMM_BLOCK_K, m0, p.hint_a);
-                        else tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], 0, kb * GEMM_BLOCK_K, m0);
+                        if (p.hint_a) tma_load_2d_cg2_hint(sa, ta, &full_bar[stage], 0, kb * GEMM_BLOCK_K, m0, p.hint_a);
+                        else tma_load_2d_cg2(sa, ta, &full_bar[stage], 0, kb * GEMM_BLOCK_K, m0);
                         if (p.hint_b) tma_load_2d_cg2_hint(sb, tb, &full_bar[stage], 0, kb * GEMM_BLOCK_K, n0, p.hint_b);
                         else tma_load_2d_cg2(sb, tb, &full_bar[stage], 0, kb * GEMM_BLOCK_K, n0);
                     }
@@ -207,11 +219,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (is_leader && elect_one()) {
             constexpr uint32_t idesc_full = make_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
             constexpr uint32_t idesc_half = make_idesc_bf16(TILE_M, BLOCK_N / 2, 0, 0);
+            constexpr uint32_t idesc_narrow = make_idesc_bf16(TILE_M / 2, BLOCK_N, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
             for (int unit = cluster_id; unit < p.num_units; unit += num_clusters, ++it) {
-                const uint32_t idesc = (unit < p.full_units) ? idesc_full : idesc_half;
+                uint32_t idesc = (unit < p.full_units) ? idesc_full : idesc_half;
+                if (p.narrow_m && unit < p.full_units) {
+                    int m_blk, n_blk;
+                    tile_coords(unit, m_blk, n_blk);
+                    if (is_narrow(m_blk)) idesc = idesc_narrow;
+                }
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait<kCtaGroup == 2>(&tmem_empty_bar[acc], acc_phase ^ 1, 2);
@@ -251,9 +269,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t acc_phase = (it >> 1) & 1;
             int m_blk, n_blk;
             tile_coords(tile, m_blk, n_blk);
-            const int m0 = m_blk * TILE_M + (int)cta_rank * 128;
-            const int n0 = n_blk * BLOCK_N + (half > 0 ? BLOCK_N / 2 : 0);
-            const int row = m0 + q * 32 + lane;
+            // narrow tile (layout B): this CTA holds 64 rows; warps 0/1 own accumulator columns [0, N/2), warps 2/3 the
+            // columns [N/2, N), all at TMEM columns [0, N/2) of their own lanes
+            const bool narrow = is_narrow(m_blk);
+            const int m0 = m_blk * TILE_M + (int)cta_rank * (narrow ? 64 : 128);
+            const int n_tile0 = n_blk * BLOCK_N + (half > 0 ? BLOCK_N / 2 : 0);
+            const int col_half = narrow ? (q >> 1) : 0;
+            const int n0 = n_tile0 + col_half * (BLOCK_N / 2);          // first output column this thread handles
+            const int n_cols = narrow ? BLOCK_N / 2 : bn_eff;            // ... and how many (TMEM columns [0, n_cols))
+            const int row = m0 + (narrow ? (q & 1) : q) * 32 + lane;
             const bool row_ok = row < p.M;
             // EPI_GATED_RES: the residual row slice, the per-sample gate and the bias do not depend on the accumulator;
             // chunk c+1's loads are issued before chunk c is combined, and the first chunk's loads are issued before
@@ -282,7 +306,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if constexpr (kEpi == EPI_GATED_RES) {
                 // x' = x + bf16(bf16(acc + bias) * gate); operands prefetched above / one chunk ahead
 #pragma unroll 1
-                for (int c = 0; c < bn_eff / 32; ++c) {
+                for (int c = 0; c < n_cols / 32; ++c) {
                     uint32_t r[32];
                     tmem_ld_x32(taddr + c * 32, r);
                     uint32_t res_p[16], gate_p[16], bias_p[16];
@@ -293,7 +317,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         bias_p[4 * j] = bias_n[j].x; bias_p[4 * j + 1] = bias_n[j].y; bias_p[4 * j + 2] = bias_n[j].z; bias_p[4 * j + 3] = bias_n[j].w;
                     }
                     const int col = n0 + c * 32;
-                    if (c + 1 < bn_eff / 32) prefetch(col + 32);
+                    if (c + 1 < n_cols / 32) prefetch(col + 32);
                     tmem_ld_wait();
                     uint32_t outp[16];
 #pragma unroll
@@ -314,7 +338,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             } else if constexpr (kEpi == EPI_STORE) {
 #pragma unroll 1
-                for (int c = 0; c < bn_eff / 32; ++c) {
+                for (int c = 0; c < n_cols / 32; ++c) {
                     uint32_t r[32];
                     tmem_ld_x32(taddr + c * 32, r);
                     tmem_ld_wait();
@@ -350,7 +374,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 // weight rows are interleaved in groups of 64: [gate 64 | up 64] per 128 accumulator columns
                 static_assert(kEpi != EPI_SWIGLU || BLOCK_N % 128 == 0, "SwiGLU epilogue needs 128-column groups");
 #pragma unroll 1
-                for (int c = 0; c < bn_eff / 64; ++c) {
+                for (int c = 0; c < n_cols / 64; ++c) {
                     const int grp = c >> 1, hf = c & 1;
                     uint32_t g[32], u[32];
                     tmem_ld_x32(taddr + grp * 128 + hf * 32, g);
@@ -367,7 +391,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         outp[j] = pack_bf16x2(g0 * u0, g1 * u1);
                     }
                     if (row_ok) {
-                        const int col = n0 / 2 + grp * 64 + hf * 32;
+                        const int col = n0 / 2 + grp * 64 + hf * 32;   // n0 already includes a narrow tile's column half
                         uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + col);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)

@@ -84,6 +84,8 @@ def _install_stubs(backend: str = "cpu"):
         # the real third-party kernels: liger_kernel (Triton) as is, FA2 behind FA3's module name
         import flash_attn
         import liger_kernel.transformers  # noqa: F401  (model.py imports the real classes from it)
+        # liger 0.8.0's rms_norm references torch.distributed.tensor.DTensor without importing the submodule
+        importlib.import_module("torch.distributed.tensor")
 
         def fa2_varlen(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, softmax_scale):
             return flash_attn.flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
@@ -146,8 +148,17 @@ def build_reference_dit(cfg: dict, sd: dict, dtype=torch.float32, backend: str =
     """Instantiate the reference DiT, load ``sd`` (reference keys) and cast like users do."""
     m = load_reference_model_module(backend)
     if device is not None:
-        with torch.device(device):   # fp32 construction on the device, then the user's .to(dtype) (RoPE buffers included)
-            model = m.DiT(**cfg)
+        # fp32 construction directly on the device (a 10B-architecture init on the host takes minutes), then the user's
+        # .to(dtype) (RoPE buffers included).  model.py:342 builds inv_freq with the legacy `torch.FloatTensor([...])`
+        # constructor, which ignores the device context: route that one constructor through torch.tensor for the
+        # duration of __init__ (same fp32 values; the reference source is not touched).
+        legacy = torch.FloatTensor
+        torch.FloatTensor = lambda data: torch.tensor(data, dtype=torch.float32)
+        try:
+            with torch.device(device):
+                model = m.DiT(**cfg)
+        finally:
+            torch.FloatTensor = legacy
     else:
         model = m.DiT(**cfg)
     if sd is not None:

@@ -565,3 +565,55 @@ def test_attention_resident_kv_rejects_long_key_sequences():
     with pytest.raises(_lib.FliteError, match="precondition"):
         _lib.watchdog_ok()
     _lib.watchdog_ok()                                      # the word is cleared after it has been reported
+
+
+@pytest.mark.parametrize("M", [8224, 356, 640, 300, 4100])
+def test_gemm_narrow_last_m_tile_bit_equal(M):
+    """FLITE_TUNE_GEMM_NARROW_M: a ragged last M-tile with <= 128 valid rows runs as tcgen05 M = 128 MMAs (64 rows per
+    CTA, TMEM "layout B") instead of a padded 256-row tile.  Same bits as the padded path for the three epilogues that
+    use it, rows beyond M untouched (M = 300 has a 44-row tail, 640 a 128-row one, 356 = 256 + 100, 8224 = C2, 4100 = C4
+    per sequence-parallel rank)."""
+    from flite_b200 import _lib, ops
+    lib = _lib.load()
+    d, inter, B = 512, 1024, 2
+    g = torch.Generator(device=DEV).manual_seed(M)
+    a = (torch.randn(M, d, device=DEV, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(d, d, device=DEV, generator=g) * 0.05).bfloat16()
+    bias = torch.randn(d, device=DEV, generator=g).bfloat16()
+    gate = torch.randn(B, d, device=DEV, generator=g).bfloat16()
+    x0 = torch.randn(M + 8, d, device=DEV, generator=g).bfloat16()
+    wgu = ops.interleave_gate_up((torch.randn(inter, d, device=DEV, generator=g) * 0.05).bfloat16(),
+                                 (torch.randn(inter, d, device=DEV, generator=g) * 0.05).bfloat16())
+    a2 = (torch.randn(M, inter, device=DEV, generator=g) * 0.5).bfloat16()
+    wd = (torch.randn(d, inter, device=DEV, generator=g) * 0.05).bfloat16()
+    rps = (M + B - 1) // B
+
+    def run_all():
+        outs = []
+        o = torch.full((M + 8, d), 7.0, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(a, w, bias, variant=_lib.GEMM_2CTA_N256, out=o[:M])
+        outs.append(o)
+        x = x0.clone()
+        ops.gemm(a, w, bias, epilogue=ops.EPI_GATED_RES, resid=x[:M], gate=gate, rows_per_sample=rps,
+                 variant=_lib.GEMM_2CTA_N256, out=x[:M])
+        outs.append(x)
+        h = torch.full((M + 8, inter), 7.0, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(a, wgu, None, epilogue=ops.EPI_SWIGLU, variant=_lib.GEMM_2CTA_N256, out=h[:M])
+        outs.append(h)
+        y = x0.clone()
+        ops.gemm(a2, wd, None, epilogue=ops.EPI_GATED_RES, resid=y[:M], gate=gate, rows_per_sample=rps,
+                 variant=_lib.GEMM_2CTA_N256, out=y[:M])
+        outs.append(y)
+        return outs
+
+    narrow = run_all()
+    lib.flite_set_tuning(14, 1)
+    try:
+        padded = run_all()
+    finally:
+        lib.flite_set_tuning(14, 0)
+    for i, (n_, p_) in enumerate(zip(narrow, padded)):
+        assert torch.equal(n_, p_), f"output {i} differs between the narrow and the padded last M-tile"
+    assert bool((narrow[0][M:] == 7.0).all()) and bool((narrow[2][M:] == 7.0).all())
+    assert torch.equal(narrow[1][M:], x0[M:])
+    assert rel(narrow[0][:M], F.linear(a, w, bias)) <= 1e-3

@@ -41,6 +41,7 @@ def _record():
 def _liger():
     try:
         import liger_kernel.transformers as lt
+        import torch.distributed.tensor  # noqa: F401  (liger 0.8.0 uses torch.distributed.tensor.DTensor without importing it)
         from liger_kernel.ops import LigerSiLUMulFunction
     except Exception as e:  # pragma: no cover
         pytest.skip(f"liger_kernel not importable: {e!r}")
@@ -109,18 +110,22 @@ def test_flash_attn_restatement_and_product_kernel_vs_real_fa2(q_lens, k_lens, H
     cu_k = torch.tensor([0] + list(itertools.accumulate(k_lens)), dtype=torch.int32, device=DEV)
     scale = 256 ** -0.5
     real = fa.flash_attn_varlen_func(q, k, v, cu_q, cu_k, max(q_lens), max(k_lens), softmax_scale=scale, causal=False)
-    if min(k_lens) > 0:
-        mine = dit_oracle.flash_attn_varlen(q, k, v, cu_q, cu_k, scale)
-        r_oracle = rel(mine, real)
-    else:
-        r_oracle = None          # the restatement's softmax over zero keys is NaN; FA2 (and the product) return zeros
     ours = ops.attention_varlen(q.view(Tq, H * 256), k.view(Tk, H * 256), v.view(Tk, H * 256), cu_q, cu_k, H,
                                 max(q_lens), scale).view(Tq, H, 256)
-    r_ours = rel(ours, real)
-    _RECORD[f"fa2_q{q_lens}_k{k_lens}_h{H}"] = {"oracle_vs_fa2": r_oracle, "product_vs_fa2": r_ours}
-    if r_oracle is not None:
-        assert r_oracle <= 3e-3, r_oracle
-    assert r_ours <= 3e-3, r_ours
+    rec = {"product_vs_fa2": rel(ours, real)}
+    if min(k_lens) > 0:
+        mine = dit_oracle.flash_attn_varlen(q, k, v, cu_q, cu_k, scale)                       # bf16 out, fp32 softmax
+        exact = dit_oracle.flash_attn_varlen(q.float(), k.float(), v.float(), cu_q, cu_k, scale)  # fp32 out
+        rec.update(oracle_vs_fa2=rel(mine, real), fa2_vs_exact=rel(real, exact), product_vs_exact=rel(ours, exact))
+    _RECORD[f"fa2_q{q_lens}_k{k_lens}_h{H}"] = rec
+    # (the restatement's softmax over zero keys is NaN; FA2 and the product return zeros there -- checked below)
+    if min(k_lens) > 0:
+        # the restatement differs from the real kernel only by FA2's own bf16-P / bf16-output error (~2.0-2.5e-3 here)
+        assert rec["oracle_vs_fa2"] <= 3e-3, rec
+        # the product's kernel also keeps P in bf16: it must be as close to the exact result as FA2 is, and the two
+        # independent bf16-P kernels differ by at most the sum of their errors
+        assert rec["product_vs_exact"] <= max(1.25 * rec["fa2_vs_exact"], 2e-3), rec
+    assert rec["product_vs_fa2"] <= 5e-3, rec
     if min(k_lens) == 0:         # rows of the sequence without keys are exactly zero in both
         z0 = sum(q_lens[:k_lens.index(0)])
         z1 = z0 + q_lens[k_lens.index(0)]
