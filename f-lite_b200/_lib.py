@@ -42,6 +42,8 @@ SIGNATURES = {
     "flite_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _I, _I, _P, _L, _P, _L, _I, _P, _P, _I, _F,
                         _I, _I, _I, _P],
     "flite_attention_varlen": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _I, _F, _I, _P],
+    "flite_attention_streamk_workspace_bytes": [],
+    "flite_attention_streamk": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P, _L, _P],
     "flite_gemm_qkv_p2p": [_P, _L, _P, _L, _I, _I, _P, _I, _P, _P, _F, _I, _I, _I, _I, _P, _I, _P],
     "flite_attention_varlen_p2p": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _I, _I, _I, _L, _P, _P, _I, _I, _I,
                                    _F, _I, _P],
@@ -76,7 +78,8 @@ def load() -> ctypes.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        fn.restype = c_char_p if name == "flite_last_error" else c_int
+        fn.restype = (c_char_p if name == "flite_last_error"
+                      else c_int64 if name == "flite_attention_streamk_workspace_bytes" else c_int)
     _lib = lib
     return lib
 

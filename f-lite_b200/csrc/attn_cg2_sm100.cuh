@@ -101,8 +101,8 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 const int krow = k_beg + j * 128;
                 mbar_wait<true>(&k_empty[st], ph, 21);
                 if (is_leader) mbar_arrive_expect_tx(&k_full[st], 2 * 32768);
-#pragma unroll
                 const int kn_half = (j == n_tiles - 1 ? tail_n : 128) >> 1;   // keys of this tile staged per CTA
+#pragma unroll
                 for (int c = 0; c < 4; ++c)   // this CTA's 64 key rows, 4 chunks of 64 head-dim columns
                     tma_load_2d_cg2(smem + ATT2_SK + st * 32768 + c * 8192, &tmap_k, &k_full[st], 0,
                                     p.k_col0 + h * 256 + c * 64, krow + (int)cta_rank * kn_half);
@@ -241,10 +241,12 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 }
             }
             l = l * corr + (rs0 + rs1);
-            // P_{j-1} V_{j-1} must be complete before P (smem) or O (TMEM) are touched
-            // smem P: P_{j-1} V_{j-1} must be complete before P is overwritten.  TMEM P lives in S_j's own columns,
-            // so only an O rescale has to wait for the previous PV.
-            if (j > 0 && (!kPTmem || need_any)) {
+            // smem P: P_{j-1} V_{j-1} must be complete before P is overwritten.  TMEM P lives in S_j's own columns, so only an
+            // O rescale NEEDS the previous PV -- but every phase of pv_done is still consumed, in order: a parity wait is
+            // only meaningful while the barrier is in the awaited phase or the one after it, and the epilogue's wait for
+            // the last phase must not be able to run two phases ahead of a skipped one.  PV_{j-1} started when S_j
+            // retired, so by this point it is normally done and the wait is free.
+            if (j > 0) {
                 mbar_wait<true>(pv_done, (j - 1) & 1, 28);
                 tc_fence_after();
                 if (need_any) {

@@ -14,6 +14,7 @@
 #include "attn_cg2_sm100.cuh"
 #include "attn_xres_sm100.cuh"
 #include "attn_qtmem_sm100.cuh"
+#include "attn_sk_sm100.cuh"
 #include "attn_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
@@ -271,9 +272,10 @@ int flite_watchdog_status(unsigned int* code_out) {
     if (code != 0) {
         CUDA_TRY(cudaMemcpyToSymbol(g_flite_abort, &zero, sizeof(zero)));
         const unsigned tag = (code >> 16) & 0x7fff;
-        if (tag >= 96 && tag <= 98)
-            return fail(FLITE_ERR_WATCHDOG, "kernel precondition failed (tag %u: 96 = a sequence has more than 256 keys in the "
-                        "resident-K/V attention, 97 / 98 = shared-memory window misaligned)", tag);
+        if (tag >= 94 && tag <= 98)
+            return fail(FLITE_ERR_WATCHDOG, "kernel precondition failed (tag %u: 94 = stream-K share shorter than a unit, 95 = "
+                        "stream-K attention called with non-uniform sequence lengths, 96 = a sequence has more than 256 keys "
+                        "in the resident-K/V attention, 97 / 98 = shared-memory window misaligned)", tag);
         return fail(FLITE_ERR_WATCHDOG, "kernel barrier wait timed out: tag %u block %u", tag, code & 0xffff);
     }
     return 0;
@@ -780,6 +782,86 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
                            int variant, void* stream) {
     return attention_impl(q, ldq, rows_q, q_col0, k, ldk, rows_k, k_col0, v, ldv, v_col0, out, ldo, cu_q, cu_k, B, H,
                           max_q, softmax_scale, variant, stream, nullptr);
+}
+
+// Persistent stream-K self-attention for uniform sequence lengths (attn_sk_sm100.cuh).  The workspace holds the flags and
+// one partial-result slot per cluster; it must be zero-filled once when it is allocated (flags are reset by their reader).
+static int sk_clusters() {
+    // one wave of co-resident 2-CTA clusters with the kernel's real footprint (the GPC layout can strand an SM)
+    static int n_dev[64] = {0};
+    int& n = n_dev[cur_dev()];
+    if (n == 0) {
+        cudaFuncSetAttribute(attn_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(num_sms() / 2 * 2);
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = ATT_SMEM;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int active = 0;
+        if (cudaOccupancyMaxActiveClusters(&active, attn_sk_kernel, &cfg) != cudaSuccess || active <= 0) {
+            cudaGetLastError();
+            active = num_sms() / 2;
+        }
+        n = active < num_sms() / 2 ? active : num_sms() / 2;
+        if (n > SK_MAX_CLUSTERS) n = SK_MAX_CLUSTERS;
+    }
+    return n;
+}
+
+int64_t flite_attention_streamk_workspace_bytes(void) {
+    return (int64_t)SK_FLAG_BYTES + (int64_t)(num_sms() / 2 + 1) * SK_SLOT_FLOATS * (int64_t)sizeof(float);
+}
+
+int flite_attention_streamk(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                            int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
+                            const int* cu_q, const int* cu_k, int B, int H, int q_len, int k_len, float softmax_scale,
+                            void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!q || !k || !v || !out || !cu_q || !cu_k || !workspace) return fail(FLITE_ERR_INVALID, "attention_streamk: null pointer");
+    if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || q_col0 % 8 || k_col0 % 8 || v_col0 % 8)
+        return fail(FLITE_ERR_INVALID, "attention_streamk: strides / column offsets must be multiples of 8");
+    if (B <= 0 || H <= 0 || q_len <= 0 || k_len <= 0)
+        return fail(FLITE_ERR_INVALID, "attention_streamk: needs B, H, q_len, k_len > 0 (uniform sequence lengths)");
+    if (rows_q < (int64_t)B * q_len || rows_k < (int64_t)B * k_len)
+        return fail(FLITE_ERR_INVALID, "attention_streamk: rows_q / rows_k smaller than B * length");
+    if (workspace_bytes < flite_attention_streamk_workspace_bytes() || ((uintptr_t)workspace & 15))
+        return fail(FLITE_ERR_INVALID, "attention_streamk: workspace too small or misaligned (flite_attention_streamk_workspace_bytes)");
+    const int64_t q_cols = (int64_t)q_col0 + 256ll * H, k_cols = (int64_t)k_col0 + 256ll * H, v_cols = (int64_t)v_col0 + 256ll * H;
+    if (q_cols > ldq || k_cols > ldk || v_cols > ldv)
+        return fail(FLITE_ERR_INVALID, "attention_streamk: col0 + 256*H exceeds the row stride");
+    CUtensorMap tq, tk, tv;
+    int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)q_cols, (uint64_t)ldq, 128);
+    if (rc) return rc;
+    rc = make_tmap(&tk, k, (uint64_t)rows_k, (uint64_t)k_cols, (uint64_t)ldk, 64);
+    if (rc) return rc;
+    rc = make_tmap(&tv, v, (uint64_t)rows_k, (uint64_t)v_cols, (uint64_t)ldv, 128);
+    if (rc) return rc;
+    AttnSkParams p;
+    p.cu_q = cu_q; p.cu_k = cu_k;
+    p.out = (__nv_bfloat16*)out; p.ldo = ldo;
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+    p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    p.B = B; p.H = H; p.q_len = q_len; p.k_len = k_len;
+    p.QT = (q_len + 255) / 256; p.NT = (k_len + 127) / 128;
+    const long long units = (long long)B * H * p.QT;
+    p.total = units * p.NT;
+    p.flags = (unsigned int*)workspace;
+    p.slots = (float*)((char*)workspace + SK_FLAG_BYTES);
+    long long clusters = sk_clusters();
+    if (clusters > units) clusters = units;     // a share is never shorter than one unit => a unit has at most two parts
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = ATT_SMEM;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    cfg.attrs = attr;
+    cfg.numAttrs = fill_launch_attrs(attr, 2);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_sk_kernel, tq, tk, tv, p));
+    return 0;
 }
 
 int flite_attention_varlen_p2p(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,

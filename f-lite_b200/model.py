@@ -20,6 +20,7 @@ K,V hoisted out of the step loop (K13).
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 from typing import Optional
 
@@ -181,6 +182,9 @@ class DiT(nn.Module):
         self._ctx_cache = None
         self._freqs = None
         self.hoist_context = True
+        # self-attention as one persistent stream-K wave (flite_attention_streamk); FLITE_ATTN_STREAMK=0 selects the
+        # one-cluster-per-query-tile kernel (flite_attention_varlen) for A/B
+        self.attn_streamk = os.environ.get("FLITE_ATTN_STREAMK", "1") != "0"
         self.gemm_variant = GEMM_AUTO
         self.sp_group = None      # Ulysses sequence-parallel process group (see enable_sequence_parallel)
         self.sp_fused = False     # exchanges fused into the kernels over NVLink peer memory instead of NCCL
@@ -478,7 +482,10 @@ class DiT(nn.Module):
             if sp is None:
                 ops.gemm(nbuf, sa.qkv.weight, sa.qkv.bias, epilogue=EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin,
                          qk_cols=2 * d, rows_per_sample=Lq, variant=v, out=qkv)
-                ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu_x, cu_x, nh, L, scale, out=abuf)
+                if self.attn_streamk:   # every image sequence has L tokens: one persistent stream-K wave
+                    ops.attention_streamk(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu_x, cu_x, nh, L, L, scale, out=abuf)
+                else:
+                    ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu_x, cu_x, nh, L, scale, out=abuf)
             elif self.sp_fused:
                 # Ulysses over peer memory: the QKV epilogue stores each head into its owner's receive buffer, the
                 # attention epilogue stores each query row into the token owner's buffer; flags order the kernels.
@@ -498,8 +505,12 @@ class DiT(nn.Module):
                 for b in range(B):
                     dist.all_to_all_single(a2a_recv[b], a2a_send[b], group=sp)
                 r2 = a2a_recv.view(B * L, 3 * dq)
-                ops.attention_varlen(r2[:, :dq], r2[:, dq:2 * dq], r2[:, 2 * dq:], cu_full, cu_full, hq, L, scale,
-                                     out=ao_full.view(B * L, dq))
+                if self.attn_streamk:
+                    ops.attention_streamk(r2[:, :dq], r2[:, dq:2 * dq], r2[:, 2 * dq:], cu_full, cu_full, hq, L, L, scale,
+                                          out=ao_full.view(B * L, dq))
+                else:
+                    ops.attention_varlen(r2[:, :dq], r2[:, dq:2 * dq], r2[:, 2 * dq:], cu_full, cu_full, hq, L, scale,
+                                         out=ao_full.view(B * L, dq))
                 for b in range(B):
                     dist.all_to_all_single(ao_recv[b], ao_full[b], group=sp)
                 for b in range(B):   # [source rank][token][dq] -> [token][source rank * dq] = head-major columns

@@ -180,6 +180,16 @@ int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col
                            int64_t ldo, const int* cu_q, const int* cu_k, int B, int H, int max_q,
                            float softmax_scale, int variant, void* stream);
 
+/* Same attention for UNIFORM sequence lengths (every sequence q_len queries / k_len keys -- the DiT's image stream),
+ * as ONE persistent wave of 2-CTA clusters with stream-K work shares: units x key-tiles are cut into equal contiguous
+ * shares, a unit split between two clusters is merged through `workspace` (flite_attention_streamk_workspace_bytes()
+ * bytes, 16-byte aligned, zero-filled ONCE by the caller when allocated; the kernel leaves it zeroed).   model.py:203-211 */
+int64_t flite_attention_streamk_workspace_bytes(void);
+int flite_attention_streamk(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                            int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out,
+                            int64_t ldo, const int* cu_q, const int* cu_k, int B, int H, int q_len, int k_len,
+                            float softmax_scale, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- fused compute + exchange over NVLink peer memory (Ulysses sequence parallelism) ----
  * flite_gemm_qkv_p2p: the QKV projection (+bias, RoPE, QK-norm) whose epilogue stores every head straight into the
  *   receive buffer of the rank that owns it: peer_recv[g][(sample*seq_len + sp_rank*tokens_per_sample + t), q|k|v][..]

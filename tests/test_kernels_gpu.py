@@ -617,3 +617,50 @@ def test_gemm_narrow_last_m_tile_bit_equal(M):
     assert bool((narrow[0][M:] == 7.0).all()) and bool((narrow[2][M:] == 7.0).all())
     assert torch.equal(narrow[1][M:], x0[M:])
     assert rel(narrow[0][:M], F.linear(a, w, bias)) <= 1e-3
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(2, 12, 4112, 4112), (4, 12, 600, 600), (2, 12, 1024, 300), (2, 2, 272, 272),
+                                       (3, 4, 1000, 129), (1, 3, 16400, 16400)])
+def test_attention_streamk_matches_general_kernel(B, H, Lq, Lk):
+    """flite_attention_streamk (persistent stream-K wave, uniform lengths) vs flite_attention_varlen (one cluster per
+    256-query tile): units that one cluster computes alone give the same bits; a unit split between two clusters is
+    merged in fp32, so it may differ by a bf16 ulp.  Also vs the fp32 oracle, and a second launch must reproduce the
+    first bit for bit (the merge flags are reset by their reader)."""
+    from flite_b200 import ops
+    from oracle import dit_oracle
+    d = H * 256
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + Lq)
+    q = torch.randn(B * Lq, H, 256, device=DEV, generator=g)
+    k = torch.randn(B * Lk, H, 256, device=DEV, generator=g)
+    q = (q * torch.rsqrt(q.pow(2).mean(-1, keepdim=True) + 1e-6)).bfloat16().view(B * Lq, d)
+    k = (k * torch.rsqrt(k.pow(2).mean(-1, keepdim=True) + 1e-6)).bfloat16().view(B * Lk, d)
+    v = torch.randn(B * Lk, d, device=DEV, generator=g).bfloat16()
+    cu_q = (torch.arange(B + 1, dtype=torch.int32) * Lq).to(DEV)
+    cu_k = (torch.arange(B + 1, dtype=torch.int32) * Lk).to(DEV)
+    scale = 256 ** -0.5
+    base = ops.attention_varlen(q, k, v, cu_q, cu_k, H, Lq, scale)
+    out = torch.full((B * Lq + 4, d), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.attention_streamk(q, k, v, cu_q, cu_k, H, Lq, Lk, scale, out=out[:B * Lq])
+    again = ops.attention_streamk(q, k, v, cu_q, cu_k, H, Lq, Lk, scale)
+    from flite_b200 import _lib
+    _lib.watchdog_ok()
+    assert bool((out[B * Lq:] == 7.0).all())
+    assert torch.equal(out[:B * Lq], again)
+    eq = (out[:B * Lq] == base).float().mean().item()
+    r = rel(out[:B * Lq], base)
+    print(f"streamk vs general: bit-equal {eq:.4f} rel {r:.2e}")
+    assert r <= 2e-3 and eq > 0.5
+    if B * Lq * Lk * H <= 2 * 12 * 4112 * 4112:
+        ref = dit_oracle.flash_attn_varlen(q.view(-1, H, 256).float(), k.view(-1, H, 256).float(),
+                                           v.view(-1, H, 256).float(), cu_q, cu_k, scale).reshape(-1, d)
+        assert rel(out[:B * Lq], ref) <= 5e-3
+
+
+def test_attention_streamk_rejects_ragged_lengths():
+    from flite_b200 import _lib, ops
+    H, d = 2, 512
+    q = rnd(600, d); k = rnd(600, d); v = rnd(600, d)
+    cu = torch.tensor([0, 280, 600], dtype=torch.int32, device=DEV)      # 280 + 320, not 2 x 300
+    ops.attention_streamk(q, k, v, cu, cu, H, 300, 300, 256 ** -0.5)
+    with pytest.raises(_lib.FliteError):
+        _lib.watchdog_ok()
