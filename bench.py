@@ -547,6 +547,19 @@ def multi_gpu_layouts(model, dev, world, rank, steps):
             h = torch.tensor([rep.get("p2p signal+wait", (0, 0.0))[1]], device=dev, dtype=torch.float64)
             dist.all_reduce(h, op=dist.ReduceOp.MAX)
             hs = float(h.item())
+        # same layout with the stream-K self-attention where its heuristic picks it (model.attn_streamk = "auto": long
+        # sequences whose per-tile grid wastes >= 10 % of its last wave).  Not batch-invariant, hence a separate number.
+        sk = None
+        if sp_group is not None and model._use_streamk_auto(1 if cfg_group is not None else 2,
+                                                            arch["num_heads"] // sp_ranks, 16 + (height // 16) * (width // 16)):
+            model.attn_streamk = "auto"
+            lat, acc = lat0.clone(), lat0.clone()
+            v_sk = flite_b200.denoise_step(model, lat, acc, ctx_in, mask_in, t_in, 0.01, GUIDANCE, True, cfg_group=cfg_group).clone()
+            r_sk = torch.tensor([rel(v_sk, v1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(r_sk, op=dist.ReduceOp.MAX)
+            ms_sk = timed(step, n)
+            model.attn_streamk = "0"
+            sk = {"ms_per_step": ms_sk, "speedup_vs_1gpu": ms1 / ms_sk, "rel_l2_vs_1gpu": float(r_sk.item())}
         _lib.watchdog_ok()
         model.enable_sequence_parallel(None)
         name = "x".join(p for p in ((f"cfg{cfg_ranks}" if cfg_ranks > 1 else ""), (f"sp{sp_ranks}" if sp_ranks > 1 else "")) if p)
@@ -557,7 +570,8 @@ def multi_gpu_layouts(model, dev, world, rank, steps):
                                     (" + " if sp_ranks > 1 and cfg_ranks > 1 else "") +
                                     ("CFG halves on different GPUs: one NCCL all-gather of the velocity per step" if cfg_ranks > 1 else ""),
                         "ms_per_step": ms, "ms_per_step_1gpu": ms1, "speedup_vs_1gpu": ms1 / ms,
-                        "rel_l2_vs_1gpu": float(r.item()), "handshake_ms_per_step": hs, "steps_timed": n})
+                        "rel_l2_vs_1gpu": float(r.item()), "handshake_ms_per_step": hs, "steps_timed": n,
+                        "with_streamk_attention": sk})
     return results
 
 

@@ -44,6 +44,8 @@ SIGNATURES = {
     "flite_attention_varlen": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _I, _F, _I, _P],
     "flite_attention_streamk_workspace_bytes": [],
     "flite_attention_streamk": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P, _L, _P],
+    "flite_attention_streamk_p2p": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _I, _I, _I, _L, _P, _P, _I, _I, _I, _I, _F,
+                                    _P, _L, _P],
     "flite_gemm_qkv_p2p": [_P, _L, _P, _L, _I, _I, _P, _I, _P, _P, _F, _I, _I, _I, _I, _P, _I, _P],
     "flite_attention_varlen_p2p": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _I, _I, _I, _L, _P, _P, _I, _I, _I,
                                    _F, _I, _P],

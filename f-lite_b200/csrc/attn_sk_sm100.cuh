@@ -40,6 +40,12 @@ struct AttnSkParams {
     long long total;       // B * H * QT * NT tile-steps
     unsigned int* flags;   // workspace head: [cluster slot][cta rank], zero when idle
     float* slots;          // workspace body: [cluster slot][SK_SLOT_FLOATS]
+    // Fused Ulysses return path (as in attn_fwd_cg2_kernel): when out_peer[0] != nullptr query row l of this rank's heads
+    // is stored into the token owner's buffer over NVLink peer memory, out_peer[l / sp_lq][(b*sp_lq + l % sp_lq), sp_head0 + h],
+    // as whole 256-byte row segments (each warp transposes its 32 rows through the otherwise unused P region of smem).
+    __nv_bfloat16* out_peer[8];
+    int sp_lq;
+    int sp_head0;
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -302,6 +308,67 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const bool row_ok = row_in_seq < p.q_len;
             const bool is_writer = j0 > 0;             // this cluster owns the unit's LAST key tiles: publish a partial
             const bool is_reader = j1 < NT;            // ... the FIRST key tiles: merge the partner's partial and finish
+            // final rows of this unit: out = O * w1 (+ partner partial * w2), bf16; local rows are stored directly, rows
+            // that belong to a peer GPU are staged through smem and leave as whole 256-byte segments
+            auto emit_rows = [&](float w1, float w2, const float4* prow) {
+                __nv_bfloat16* orow = p.out + (long long)(p.cu_q[b] + row_in_seq) * p.ldo + h * 256;
+                const bool to_peer = p.out_peer[0] != nullptr;
+                if (to_peer && row_ok) {
+                    const int owner = row_in_seq / p.sp_lq, li = row_in_seq - owner * p.sp_lq;
+                    orow = p.out_peer[owner] + ((long long)b * p.sp_lq + li) * p.ldo + (p.sp_head0 + h) * 256;
+                }
+                uint8_t* stg = smem + ATT2_SP + (warp_idx - 2) * (32 * 256);      // 32 rows x 128 columns per warp
+                const unsigned long long my_ptr = row_ok ? (unsigned long long)orow : 0ull;
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t o[32];
+                    tmem_ld_x32(tmem_o + lane_off + c * 32, o);
+                    float4 pv[8];
+                    if (prow != nullptr) {
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) pv[x] = __ldcg(prow + c * 8 + x);
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) pv[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    tmem_ld_wait();
+                    uint4 w[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const float4 pa = pv[2 * x], pb = pv[2 * x + 1];
+                        w[x] = make_uint4(
+                            pack_bf16x2(__uint_as_float(o[8 * x]) * w1 + pa.x * w2, __uint_as_float(o[8 * x + 1]) * w1 + pa.y * w2),
+                            pack_bf16x2(__uint_as_float(o[8 * x + 2]) * w1 + pa.z * w2, __uint_as_float(o[8 * x + 3]) * w1 + pa.w * w2),
+                            pack_bf16x2(__uint_as_float(o[8 * x + 4]) * w1 + pb.x * w2, __uint_as_float(o[8 * x + 5]) * w1 + pb.y * w2),
+                            pack_bf16x2(__uint_as_float(o[8 * x + 6]) * w1 + pb.z * w2, __uint_as_float(o[8 * x + 7]) * w1 + pb.w * w2));
+                    }
+                    if (!to_peer) {
+                        if (row_ok) {
+                            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) dst[x] = w[x];
+                        }
+                        continue;
+                    }
+                    // stage: lane = row on the way in (16-byte chunks XOR-swizzled by the row), 128 columns per pass
+                    const int cc = c & 3;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+                        *reinterpret_cast<uint4*>(stg + lane * 256 + (((cc * 4 + x) ^ (lane & 15)) << 4)) = w[x];
+                    if (cc == 3) {
+                        __syncwarp();
+                        const int ch = lane & 15;                     // 16-byte chunk of the 256-byte segment
+#pragma unroll 4
+                        for (int i2 = 0; i2 < 16; ++i2) {
+                            const int rr = 2 * i2 + (lane >> 4);
+                            const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 256 + ((ch ^ (rr & 15)) << 4));
+                            const unsigned long long rp = __shfl_sync(0xffffffffu, my_ptr, rr);
+                            if (rp != 0ull) reinterpret_cast<uint4*>(rp)[(c >> 2) * 16 + ch] = v;
+                        }
+                        __syncwarp();
+                    }
+                }
+            };
             if (is_writer && is_reader) {              // a share shorter than one unit: the host never launches that
                 if (lane == 0) atomicCAS(&g_flite_abort, 0u, (94u << 16) | 0x80000000u);
             }
@@ -351,49 +418,11 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 const float inv = 1.0f / (a1 * l + a2 * l2);
                 const float w1 = a1 * inv, w2 = a2 * inv;
                 const float4* prow = reinterpret_cast<const float4*>(slot + (long long)srow * 256);
-                __nv_bfloat16* orow = p.out + (long long)(p.cu_q[b] + row_in_seq) * p.ldo + h * 256;
-#pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
-                    uint32_t o[32];
-                    tmem_ld_x32(tmem_o + lane_off + c * 32, o);
-                    float4 pv[8];
-#pragma unroll
-                    for (int x = 0; x < 8; ++x) pv[x] = __ldcg(prow + c * 8 + x);
-                    tmem_ld_wait();
-                    if (row_ok) {
-                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) {
-                            const float4 pa = pv[2 * x], pb = pv[2 * x + 1];
-                            dst[x] = make_uint4(
-                                pack_bf16x2(__uint_as_float(o[8 * x]) * w1 + pa.x * w2, __uint_as_float(o[8 * x + 1]) * w1 + pa.y * w2),
-                                pack_bf16x2(__uint_as_float(o[8 * x + 2]) * w1 + pa.z * w2, __uint_as_float(o[8 * x + 3]) * w1 + pa.w * w2),
-                                pack_bf16x2(__uint_as_float(o[8 * x + 4]) * w1 + pb.x * w2, __uint_as_float(o[8 * x + 5]) * w1 + pb.y * w2),
-                                pack_bf16x2(__uint_as_float(o[8 * x + 6]) * w1 + pb.z * w2, __uint_as_float(o[8 * x + 7]) * w1 + pb.w * w2));
-                        }
-                    }
-                }
+                emit_rows(w1, w2, prow);
                 named_bar_sync(1, 128);                // every row of this CTA has consumed the partial
                 if (r == 0) *const_cast<volatile unsigned int*>(f) = 0u;   // idle again (graph replay / next launch)
             } else {
-                const float inv_l = 1.0f / l;
-                __nv_bfloat16* orow = p.out + (long long)(p.cu_q[b] + row_in_seq) * p.ldo + h * 256;
-#pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
-                    uint32_t o[32];
-                    tmem_ld_x32(tmem_o + lane_off + c * 32, o);
-                    tmem_ld_wait();
-                    if (row_ok) {
-                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-                        for (int x = 0; x < 4; ++x)
-                            dst[x] = make_uint4(
-                                pack_bf16x2(__uint_as_float(o[8 * x]) * inv_l, __uint_as_float(o[8 * x + 1]) * inv_l),
-                                pack_bf16x2(__uint_as_float(o[8 * x + 2]) * inv_l, __uint_as_float(o[8 * x + 3]) * inv_l),
-                                pack_bf16x2(__uint_as_float(o[8 * x + 4]) * inv_l, __uint_as_float(o[8 * x + 5]) * inv_l),
-                                pack_bf16x2(__uint_as_float(o[8 * x + 6]) * inv_l, __uint_as_float(o[8 * x + 7]) * inv_l));
-                    }
-                }
+                emit_rows(1.0f / l, 0.f, nullptr);
             }
             tc_fence_before();     // this segment's TMEM reads are ordered before the p_full arrival of the next one
             g0 += n;

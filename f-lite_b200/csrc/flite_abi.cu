@@ -816,10 +816,12 @@ int64_t flite_attention_streamk_workspace_bytes(void) {
     return (int64_t)SK_FLAG_BYTES + (int64_t)(num_sms() / 2 + 1) * SK_SLOT_FLOATS * (int64_t)sizeof(float);
 }
 
-int flite_attention_streamk(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
-                            int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
-                            const int* cu_q, const int* cu_k, int B, int H, int q_len, int k_len, float softmax_scale,
-                            void* workspace, int64_t workspace_bytes, void* stream) {
+struct AttnPeers;
+static int attention_streamk_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                                  int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
+                                  const int* cu_q, const int* cu_k, int B, int H, int q_len, int k_len, float softmax_scale,
+                                  void* workspace, int64_t workspace_bytes, void* stream, void* const* peer_out,
+                                  int n_peers, int tokens_per_rank, int head0) {
     if (!q || !k || !v || !out || !cu_q || !cu_k || !workspace) return fail(FLITE_ERR_INVALID, "attention_streamk: null pointer");
     if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || q_col0 % 8 || k_col0 % 8 || v_col0 % 8)
         return fail(FLITE_ERR_INVALID, "attention_streamk: strides / column offsets must be multiples of 8");
@@ -850,6 +852,16 @@ int flite_attention_streamk(const void* q, int64_t ldq, int64_t rows_q, int q_co
     p.total = units * p.NT;
     p.flags = (unsigned int*)workspace;
     p.slots = (float*)((char*)workspace + SK_FLAG_BYTES);
+    for (int i = 0; i < 8; ++i) p.out_peer[i] = nullptr;
+    p.sp_lq = 1; p.sp_head0 = 0;
+    if (peer_out) {
+        if (n_peers <= 0 || n_peers > 8 || tokens_per_rank <= 0) return fail(FLITE_ERR_INVALID, "attention_streamk: bad peer table");
+        for (int i = 0; i < n_peers; ++i) {
+            if (!peer_out[i]) return fail(FLITE_ERR_INVALID, "attention_streamk: null peer buffer %d", i);
+            p.out_peer[i] = (__nv_bfloat16*)peer_out[i];
+        }
+        p.sp_lq = tokens_per_rank; p.sp_head0 = head0;
+    }
     long long clusters = sk_clusters();
     if (clusters > units) clusters = units;     // a share is never shorter than one unit => a unit has at most two parts
     cudaLaunchConfig_t cfg = {};
@@ -862,6 +874,25 @@ int flite_attention_streamk(const void* q, int64_t ldq, int64_t rows_q, int q_co
     cfg.numAttrs = fill_launch_attrs(attr, 2);
     CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_sk_kernel, tq, tk, tv, p));
     return 0;
+}
+
+int flite_attention_streamk(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                            int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
+                            const int* cu_q, const int* cu_k, int B, int H, int q_len, int k_len, float softmax_scale,
+                            void* workspace, int64_t workspace_bytes, void* stream) {
+    return attention_streamk_impl(q, ldq, rows_q, q_col0, k, ldk, rows_k, k_col0, v, ldv, v_col0, out, ldo, cu_q, cu_k, B, H,
+                                  q_len, k_len, softmax_scale, workspace, workspace_bytes, stream, nullptr, 0, 0, 0);
+}
+
+int flite_attention_streamk_p2p(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                                int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0,
+                                void* const* peer_out, int n_peers, int tokens_per_rank, int head0, int64_t ldo,
+                                const int* cu_q, const int* cu_k, int B, int H, int q_len, int k_len, float softmax_scale,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!peer_out) return fail(FLITE_ERR_INVALID, "attention_streamk_p2p: null peer table");
+    return attention_streamk_impl(q, ldq, rows_q, q_col0, k, ldk, rows_k, k_col0, v, ldv, v_col0, peer_out[0], ldo, cu_q, cu_k,
+                                  B, H, q_len, k_len, softmax_scale, workspace, workspace_bytes, stream, peer_out, n_peers,
+                                  tokens_per_rank, head0);
 }
 
 int flite_attention_varlen_p2p(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,

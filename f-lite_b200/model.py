@@ -182,9 +182,15 @@ class DiT(nn.Module):
         self._ctx_cache = None
         self._freqs = None
         self.hoist_context = True
-        # self-attention as one persistent stream-K wave (flite_attention_streamk); FLITE_ATTN_STREAMK=0 selects the
-        # one-cluster-per-query-tile kernel (flite_attention_varlen) for A/B
-        self.attn_streamk = os.environ.get("FLITE_ATTN_STREAMK", "1") != "0"
+        # Self-attention as one persistent stream-K wave (flite_attention_streamk) instead of one cluster per query tile.
+        # OFF by default: (1) a unit split between two clusters is merged in fp32, so the result depends on where the
+        # shares fall, i.e. on the batch size / head count -- the default path is batch-invariant, which is what makes
+        # the multi-GPU layouts bit-identical to the 1-GPU path; (2) measured (profiles/r2_attn_bench.json): it loses
+        # 8 % at C2 (the 74 clusters no longer walk the same key tiles in lock step, so K/V tiles stop being shared in
+        # L2), wins 1 % at C4 and 9 % on a sequence-parallel rank's 3 heads x 16400 tokens (390 units = 5.27 waves).
+        # "auto" (FLITE_ATTN_STREAMK=auto) turns it on when the per-tile grid wastes >= 10 % of its last wave on long
+        # sequences; "1" forces it.
+        self.attn_streamk = os.environ.get("FLITE_ATTN_STREAMK", "0")
         self.gemm_variant = GEMM_AUTO
         self.sp_group = None      # Ulysses sequence-parallel process group (see enable_sequence_parallel)
         self.sp_fused = False     # exchanges fused into the kernels over NVLink peer memory instead of NCCL
@@ -232,6 +238,20 @@ class DiT(nn.Module):
             ao = sym.local[recv_elems:recv_elems + B * Lq * d].view(B * Lq, d)
             self._sp_sym = (key, sym, recv, ao, sym.table(0), sym.table(2 * recv_elems))
         return self._sp_sym[1:]
+
+    def _use_streamk(self, B, heads, L):
+        mode = self.attn_streamk
+        if mode in (True, "1", 1):
+            return True
+        if mode != "auto":
+            return False
+        return self._use_streamk_auto(B, heads, L)
+
+    def _use_streamk_auto(self, B, heads, L):
+        units = B * heads * ((L + 255) // 256)
+        slots = max(1, torch.cuda.get_device_properties(self.device).multi_processor_count // 2)
+        waves = units / slots
+        return L >= 8192 and units >= slots and math.ceil(waves) / waves >= 1.10
 
     def _check_ready(self):
         w = self.context_proj.weight
@@ -482,7 +502,7 @@ class DiT(nn.Module):
             if sp is None:
                 ops.gemm(nbuf, sa.qkv.weight, sa.qkv.bias, epilogue=EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin,
                          qk_cols=2 * d, rows_per_sample=Lq, variant=v, out=qkv)
-                if self.attn_streamk:   # every image sequence has L tokens: one persistent stream-K wave
+                if self._use_streamk(B, nh, L):   # every image sequence has L tokens: one persistent stream-K wave
                     ops.attention_streamk(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu_x, cu_x, nh, L, L, scale, out=abuf)
                 else:
                     ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu_x, cu_x, nh, L, scale, out=abuf)
@@ -491,8 +511,12 @@ class DiT(nn.Module):
                 # attention epilogue stores each query row into the token owner's buffer; flags order the kernels.
                 ops.gemm_qkv_p2p(nbuf, sa.qkv.weight, sa.qkv.bias, cos, sin, Lq, P, hq, rk, L, recv_tab, variant=v)
                 sym.exchange_done(stream)
-                ops.attention_varlen_p2p(p2p_recv[:, :dq], p2p_recv[:, dq:2 * dq], p2p_recv[:, 2 * dq:], cu_full,
-                                         cu_full, hq, L, scale, ao_tab, P, Lq, rk * hq, d)
+                if self._use_streamk(B, hq, L):
+                    ops.attention_streamk_p2p(p2p_recv[:, :dq], p2p_recv[:, dq:2 * dq], p2p_recv[:, 2 * dq:], cu_full,
+                                              cu_full, hq, L, L, scale, ao_tab, P, Lq, rk * hq, d)
+                else:
+                    ops.attention_varlen_p2p(p2p_recv[:, :dq], p2p_recv[:, dq:2 * dq], p2p_recv[:, 2 * dq:], cu_full,
+                                             cu_full, hq, L, scale, ao_tab, P, Lq, rk * hq, d)
                 sym.exchange_done(stream)
                 ops.gemm(p2p_ao, sa.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_sa,
                          rows_per_sample=Lq, variant=v, out=xs)
@@ -505,7 +529,7 @@ class DiT(nn.Module):
                 for b in range(B):
                     dist.all_to_all_single(a2a_recv[b], a2a_send[b], group=sp)
                 r2 = a2a_recv.view(B * L, 3 * dq)
-                if self.attn_streamk:
+                if self._use_streamk(B, hq, L):
                     ops.attention_streamk(r2[:, :dq], r2[:, dq:2 * dq], r2[:, 2 * dq:], cu_full, cu_full, hq, L, L, scale,
                                           out=ao_full.view(B * L, dq))
                 else:

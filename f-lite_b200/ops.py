@@ -377,10 +377,7 @@ def attention_streamk(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: t
     Tq = q.shape[0]
     if out is None:
         out = torch.empty((Tq, num_heads * 256), dtype=BF16, device=q.device)
-    ws = _SK_WS.get(q.device)
-    if ws is None:      # flags + one partial slot per cluster; zero-filled once, the kernel leaves the flags zeroed
-        ws = torch.zeros(int(lib.flite_attention_streamk_workspace_bytes()), dtype=torch.uint8, device=q.device)
-        _SK_WS[q.device] = ws
+    ws = _sk_workspace(q.device)
     B = cu_q.numel() - 1
     _lib.check(lib.flite_attention_streamk(q.data_ptr(), q.stride(0), Tq, 0, k.data_ptr(), k.stride(0), k.shape[0], 0,
                                            v.data_ptr(), v.stride(0), 0, out.data_ptr(), out.stride(0), cu_q.data_ptr(),
@@ -388,6 +385,35 @@ def attention_streamk(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: t
                                            ws.data_ptr(), ws.numel(), _stream()), "attention_streamk")
     LAUNCHES[0] += 1
     return out
+
+
+def _sk_workspace(device):
+    lib = _lib.load()
+    ws = _SK_WS.get(device)
+    if ws is None:      # flags + one partial slot per cluster; zero-filled once, the kernel leaves the flags zeroed
+        ws = torch.zeros(int(lib.flite_attention_streamk_workspace_bytes()), dtype=torch.uint8, device=device)
+        _SK_WS[device] = ws
+    return ws
+
+
+@_traced(lambda q, k, v, cu_q, cu_k, num_heads, *r, **kw: f"attention+p2p Tq={q.shape[0]} Tk={k.shape[0]} H={num_heads}")
+def attention_streamk_p2p(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_q: torch.Tensor, cu_k: torch.Tensor,
+                          num_heads: int, q_len: int, k_len: int, softmax_scale: float, peer_out, n_peers: int,
+                          tokens_per_rank: int, head0: int, ldo: int) -> None:
+    """``attention_streamk`` with the fused return all-to-all of ``attention_varlen_p2p``."""
+    lib = _lib.load()
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, n)
+    _chk(cu_q, "cu_q", torch.int32)
+    _chk(cu_k, "cu_k", torch.int32)
+    ws = _sk_workspace(q.device)
+    B = cu_q.numel() - 1
+    _lib.check(lib.flite_attention_streamk_p2p(q.data_ptr(), q.stride(0), q.shape[0], 0, k.data_ptr(), k.stride(0),
+                                               k.shape[0], 0, v.data_ptr(), v.stride(0), 0, peer_out, n_peers,
+                                               tokens_per_rank, head0, ldo, cu_q.data_ptr(), cu_k.data_ptr(), B, num_heads,
+                                               int(q_len), int(k_len), float(softmax_scale), ws.data_ptr(), ws.numel(),
+                                               _stream()), "attention_streamk_p2p")
+    LAUNCHES[0] += 1
 
 
 @_traced(lambda a, w, *r, **k: f"gemm qkv_rope+p2p {a.shape[0]}x{w.shape[0]}x{a.shape[1]}")

@@ -189,6 +189,12 @@ int flite_attention_streamk(const void* q, int64_t ldq, int64_t rows_q, int q_co
                             int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out,
                             int64_t ldo, const int* cu_q, const int* cu_k, int B, int H, int q_len, int k_len,
                             float softmax_scale, void* workspace, int64_t workspace_bytes, void* stream);
+/* ... with the fused Ulysses return path of flite_attention_varlen_p2p (rows stored into the token owner's buffer). */
+int flite_attention_streamk_p2p(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
+                                int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0,
+                                void* const* peer_out, int n_peers, int tokens_per_rank, int head0, int64_t ldo,
+                                const int* cu_q, const int* cu_k, int B, int H, int q_len, int k_len,
+                                float softmax_scale, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- fused compute + exchange over NVLink peer memory (Ulysses sequence parallelism) ----
  * flite_gemm_qkv_p2p: the QKV projection (+bias, RoPE, QK-norm) whose epilogue stores every head straight into the

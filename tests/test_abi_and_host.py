@@ -173,3 +173,65 @@ def test_pipeline_public_surface_matches_reference():
     assert o.images == [1]
     a = pipeline.APGConfig()
     assert a.enabled is True and a.orthogonal_threshold == 0.03          # pipeline.py:25-31
+
+
+def test_encode_prompt_contract_with_stand_in_encoder():
+    """Text-encoder side of the pipeline (f_lite/pipeline.py:104-175) exercised on the CPU with stand-ins for the
+    third-party processor / encoder: chat template -> processor(text=..., padding='longest', pad_to_multiple_of=8,
+    max_length=512, truncation=True) -> hidden_states[return_index]; negative prompt None => zeros (pipeline.py:160-161);
+    same 2-tuple return as the reference, masks through encode_prompt_with_masks."""
+    import torch
+    from flite_b200 import FLitePipeline
+
+    class Batch(dict):
+        def to(self, *a, **k):
+            return self
+
+    class Proc:
+        def __init__(self):
+            self.calls = []
+
+        def apply_chat_template(self, messages, tokenize=False, add_generation_prompt=True):
+            assert messages[0]["role"] == "system" and messages[1]["role"] == "user"
+            assert tokenize is False and add_generation_prompt is True
+            return "<sys>" + messages[0]["content"][:8] + "<user>" + messages[1]["content"][0]["text"]
+
+        def __call__(self, text, padding, pad_to_multiple_of, max_length, truncation, return_tensors):
+            self.calls.append(dict(text=text, padding=padding, pad_to_multiple_of=pad_to_multiple_of,
+                                   max_length=max_length, truncation=truncation, return_tensors=return_tensors))
+            lens = [len(t) % 13 + 3 for t in text]
+            L = (max(lens) + 7) // 8 * 8
+            ids = torch.zeros(len(text), L, dtype=torch.long)
+            mask = torch.zeros(len(text), L, dtype=torch.long)
+            for i, n in enumerate(lens):
+                ids[i, :n] = torch.arange(1, n + 1) + i
+                mask[i, :n] = 1
+            return Batch(input_ids=ids, attention_mask=mask)
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding(64, 32)
+            self.device = torch.device("cpu")
+
+        def forward(self, input_ids, attention_mask, use_cache, return_dict, output_hidden_states):
+            assert use_cache is False and return_dict and output_hidden_states
+            h = self.emb(input_ids)
+            from types import SimpleNamespace
+            return SimpleNamespace(hidden_states=[h * (i + 1) for i in range(12)])
+
+    proc, enc = Proc(), Enc()
+    pipe = FLitePipeline(None, None, enc, proc)
+    out = pipe.encode_prompt(["a red fox", "two cats on a sofa"], dtype=torch.float32)
+    assert isinstance(out, tuple) and len(out) == 2                     # the reference's contract (pipeline.py:175)
+    emb, neg = out
+    assert proc.calls[0]["padding"] == "longest" and proc.calls[0]["pad_to_multiple_of"] == 8
+    assert proc.calls[0]["max_length"] == 512 and proc.calls[0]["truncation"] is True
+    assert emb.shape[0] == 2 and emb.shape[1] % 8 == 0 and torch.equal(neg, torch.zeros_like(emb))
+    ids = proc(text=proc.calls[0]["text"], padding="longest", pad_to_multiple_of=8, max_length=512, truncation=True,
+               return_tensors="pt")["input_ids"]
+    assert torch.equal(emb, enc.emb(ids) * 5)                           # hidden_states[-8] of 12
+    e2, n2, m2, nm2 = pipe.encode_prompt_with_masks("a red fox", negative_prompt="blurry", dtype=torch.float32)
+    assert e2.shape[0] == 1 and n2.shape[0] == 1 and m2.dtype == torch.long and nm2.sum() > 0
+    assert not torch.equal(n2, torch.zeros_like(n2))                    # a real negative prompt is encoded, not zeros
+    assert "<user>blurry" in proc.calls[-1]["text"][0] and "<user>a red fox" in proc.calls[-2]["text"][0]

@@ -380,6 +380,34 @@ def test_fused_ulysses_kernels_single_gpu_loopback(P):
     got = torch.stack([a_.view(B, Lq, d) for a_ in ao], 1)          # [B, P, Lq, d]
     got = got.permute(0, 1, 2, 3).reshape(B, P * Lq, d).reshape(B * L, d)
     assert torch.equal(got, att)
+    # the stream-K attention with the same fused return path (too few units here for a split: same bits)
+    ao2 = [torch.zeros(B * Lq, d, device=DEV, dtype=torch.bfloat16) for _ in range(P)]
+    ao2_tab = _peer_table(ao2)
+    for r in range(P):
+        rr = recv[r]
+        ops.attention_streamk_p2p(rr[:, :dq], rr[:, dq:2 * dq], rr[:, 2 * dq:], cu, cu, Hp, L, L, scale, ao2_tab, P, Lq,
+                                  r * Hp, d)
+    for a_, b_ in zip(ao, ao2):
+        assert torch.equal(a_, b_)
+
+
+def test_attention_streamk_peer_epilogue_with_split_units():
+    """Stream-K attention with the staged peer-store epilogue at a size where units ARE split between clusters
+    (2 x 4 heads x 5 query tiles = 40 units... 12 heads: 120 units > 74 clusters): the rows written through the peer table
+    (all "peers" on this GPU) must equal the locally stored result of the same kernel."""
+    from flite_b200 import ops
+    B, H, L, P = 2, 12, 1280, 4
+    d, Lq = H * 256, L // P
+    qkv = rnd(B * L, 3 * d, scale=1.0, seed=11)
+    cu = (torch.arange(0, B + 1, dtype=torch.int32) * L).to(DEV)
+    scale = 256 ** -0.5
+    local = ops.attention_streamk(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, H, L, L, scale)
+    ao = [torch.zeros(B * Lq, d, device=DEV, dtype=torch.bfloat16) for _ in range(P)]
+    ops.attention_streamk_p2p(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, H, L, L, scale, _peer_table(ao), P, Lq, 0, d)
+    got = torch.stack([a_.view(B, Lq, d) for a_ in ao], 1).reshape(B * L, d)
+    assert torch.equal(got, local)
+    base = ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, H, L, scale)
+    assert rel(local, base) <= 2e-3
 
 
 def test_p2p_flags_signal_then_wait_loopback():
