@@ -66,6 +66,13 @@ struct GemmParams {
     // lanes 0-63 = rows 0-63 x accumulator columns [0, N/2), lanes 64-127 = the same rows x columns [N/2, N), both at
     // TMEM columns [0, N/2).
     int narrow_m;
+    // EPI_GATED_RES: when ssq_out != nullptr the epilogue also writes, for every output row, the sum of squares of the
+    // bf16 values it stored, one fp32 slot per 128 output columns: ssq_out[row * ssq_ld + col / 128].  Every slot is
+    // written exactly once per launch (whole tiles cover two slots per thread, half-width / narrow units one), so the
+    // RMSNorm that follows (rmsnorm_modulate_ssq_kernel) sums N / 128 slots in a fixed order instead of re-reading the
+    // row: deterministic, batch-invariant, and the norm becomes a single pass over x.
+    float* ssq_out;
+    long long ssq_ld;
     // L2 eviction-priority hints of the A / W tile loads (0 = plain load); chosen with the band height so that the operand
     // the rasterisation keeps resident is evict_last and the one that streams past it is evict_first.
     unsigned long long hint_a, hint_b;
@@ -305,6 +312,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
             if constexpr (kEpi == EPI_GATED_RES) {
                 // x' = x + bf16(bf16(acc + bias) * gate); operands prefetched above / one chunk ahead
+                float ss = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < n_cols / 32; ++c) {
                     uint32_t r[32];
@@ -328,12 +336,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         a = bf16_round(a * bf16_lo(gate_p[j]));
                         b = bf16_round(b * bf16_hi(gate_p[j]));
                         outp[j] = pack_bf16x2(bf16_lo(res_p[j]) + a, bf16_hi(res_p[j]) + b);
+                        const float v0 = bf16_lo(outp[j]), v1 = bf16_hi(outp[j]);     // the values as stored
+                        ss = fmaf(v0, v0, ss);
+                        ss = fmaf(v1, v1, ss);
                     }
                     if (row_ok) {
                         uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + col);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             cp[j] = make_uint4(outp[4 * j], outp[4 * j + 1], outp[4 * j + 2], outp[4 * j + 3]);
+                    }
+                    if ((c & 3) == 3) {          // a 128-column group is complete
+                        if (p.ssq_out != nullptr && row_ok) p.ssq_out[(long long)row * p.ssq_ld + (col >> 7)] = ss;
+                        ss = 0.f;
                     }
                 }
             } else if constexpr (kEpi == EPI_STORE) {
