@@ -97,7 +97,7 @@ rmsnorm_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv
     }
 }
 
-// Single-pass variant: the sum of squares of every row arrives pre-reduced in d / 128 fp32 slots written by the
+// Single-pass variant: the sum of squares of every row arrives pre-reduced in d / 64 fp32 slots written by the
 // gated-residual GEMM epilogue that produced x (GemmParams::ssq_out), so the row is read ONCE: the 16-byte loads feed
 // the normalise / modulate / store chain directly, with no reduction and no second pass in between.  The slots are
 // summed in a fixed order (lane i takes slot i, xor-shuffle tree), i.e. the result does not depend on the launch shape.
@@ -113,7 +113,7 @@ rmsnorm_modulate_ssq_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, 
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
-    const int nchunk = d >> 3, nslot = d >> 7;
+    const int nchunk = d >> 3, nslot = d >> 6;
     float part = 0.f;
     for (int i = lane; i < nslot; i += 32) part += __ldcg(ssq + (long long)row * ld_ssq + i);
     const float rstd = rsqrtf(warp_sum(part) / (float)d + eps);

@@ -165,9 +165,10 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     // one wave (needs 128-column granularity for SwiGLU pairs, whole heads for the QKV epilogue => not there)
     p.full_units = num_tiles;
     p.num_units = num_tiles;
-    const bool can_split = kEpi != EPI_QKV_ROPE && (BLOCK_N / 2) % (kEpi == EPI_SWIGLU ? 128 : 32) == 0 &&
-                           (BLOCK_N / 2 / kCtaGroup) >= 8 && g_tuning[FLITE_TUNE_GEMM_TAIL_SPLIT] == 0 &&
-                           (p.ssq_out == nullptr || (BLOCK_N / 2) % 128 == 0);   // ssq slots are 128 columns wide
+    // (a half-width unit is shared by the two epilogue warpgroups in 32-column chunks => >= 64 columns; SwiGLU needs whole
+    // 128-column [gate | up] groups)
+    const bool can_split = kEpi != EPI_QKV_ROPE && (BLOCK_N / 2) % (kEpi == EPI_SWIGLU ? 128 : 64) == 0 &&
+                           (BLOCK_N / 2 / kCtaGroup) >= 8 && g_tuning[FLITE_TUNE_GEMM_TAIL_SPLIT] == 0;
     const int tail = num_tiles % max_clusters;
     if (can_split && tail > 0 && 2 * tail <= max_clusters) {
         p.full_units = num_tiles - tail;
@@ -508,14 +509,28 @@ struct SpPeers {
     int seq_len;
 };
 
+struct NormFuse {          // fused RMSNorm + modulate of the finished rows (GemmParams::nf_*)
+    void* out;
+    int64_t ldo;
+    const void* w;
+    int wmode;
+    const void* scale;
+    const void* shift;
+    int64_t ld_mod;
+    unsigned int* counters;
+};
+
 static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
                      const void* bias, int act, int epilogue, const void* resid, int64_t ldr, const void* gate,
                      int64_t ld_gate, int rows_per_sample, const void* rope_cos, const void* rope_sin, int qk_cols,
                      float eps, int sp_ranks, int sp_heads_per_rank, int variant, void* stream, const SpPeers* peers,
-                     float* ssq_out = nullptr, int64_t ssq_ld = 0) {
+                     float* ssq_out = nullptr, int64_t ssq_ld = 0, const NormFuse* nf = nullptr) {
     if (!A || !W || !C) return fail(FLITE_ERR_INVALID, "gemm: null pointer");
-    if (ssq_out && (epilogue != EPI_GATED_RES || N % 128 || ssq_ld < N / 128))
-        return fail(FLITE_ERR_INVALID, "gemm: ssq_out needs the gated-residual epilogue, N %% 128 == 0 and ssq_ld >= N / 128");
+    if (ssq_out && (epilogue != EPI_GATED_RES || N % 64 || ssq_ld < N / 64))
+        return fail(FLITE_ERR_INVALID, "gemm: ssq_out needs the gated-residual epilogue, N %% 64 == 0 and ssq_ld >= N / 64");
+    if (nf && (!ssq_out || !nf->out || !nf->counters || nf->ldo % 8 || (nf->wmode != 0 && !nf->w) ||
+               (nf->scale == nullptr) != (nf->shift == nullptr) || nf->ld_mod % 8 || C == nf->out))
+        return fail(FLITE_ERR_INVALID, "gemm: fused norm needs ssq_out, an output buffer distinct from C, counters, and scale/shift together");
     if (M <= 0) return 0;
     if (K <= 0 || K % 64) return fail(FLITE_ERR_INVALID, "gemm: K = %d must be a positive multiple of 64", K);
     if (N <= 0 || N % 64) return fail(FLITE_ERR_INVALID, "gemm: N = %d must be a positive multiple of 64", N);
@@ -587,6 +602,12 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     p.ssq_out = ssq_out; p.ssq_ld = ssq_ld;
     if (ssq_out && variant != FLITE_GEMM_2CTA_N256 && variant != FLITE_GEMM_1CTA_N256 && variant != FLITE_GEMM_1CTA_N128)
         return fail(FLITE_ERR_INVALID, "gemm: ssq_out needs an N-tile that is a multiple of 128 columns");
+    if (nf) {
+        p.nf_out = (__nv_bfloat16*)nf->out; p.nf_ldo = nf->ldo;
+        p.nf_w = (const __nv_bfloat16*)nf->w; p.nf_wmode = nf->wmode;
+        p.nf_scale = (const __nv_bfloat16*)nf->scale; p.nf_shift = (const __nv_bfloat16*)nf->shift; p.nf_ld_mod = nf->ld_mod;
+        p.nf_counters = nf->counters;
+    }
     p.stage_stores = (epilogue == EPI_QKV_ROPE && (peers != nullptr || g_tuning[FLITE_TUNE_QKV_STAGED_STORES])) ? 1 : 0;
 
     CUtensorMap ta, tb, tbh, tah;
@@ -624,11 +645,22 @@ int flite_gemm_gated_res_ssq(const void* A, int64_t lda, const void* W, int64_t 
                      nullptr, nullptr, 0, 1e-6f, 0, 0, variant, stream, nullptr, ssq_out, ssq_ld);
 }
 
+int flite_gemm_gated_res_norm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                              const void* bias, const void* resid, int64_t ldr, const void* gate, int64_t ld_gate,
+                              int rows_per_sample, float* ssq_out, int64_t ssq_ld, void* norm_out, int64_t ld_norm_out,
+                              const void* norm_w, int weight_mode, const void* scale, const void* shift, int64_t ld_mod,
+                              float eps, unsigned int* counters, int variant, void* stream) {
+    if (!ssq_out || !norm_out || !counters) return fail(FLITE_ERR_INVALID, "gemm_gated_res_norm: null pointer");
+    NormFuse nf{norm_out, ld_norm_out, norm_w, weight_mode, scale, shift, ld_mod, counters};
+    return gemm_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, 0, EPI_GATED_RES, resid, ldr, gate, ld_gate, rows_per_sample,
+                     nullptr, nullptr, 0, eps, 0, 0, variant, stream, nullptr, ssq_out, ssq_ld, &nf);
+}
+
 int flite_rmsnorm_modulate_ssq(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w, int weight_mode,
                                const void* scale, const void* shift, int64_t ld_mod, int rows_per_sample, int rows, int d,
                                float eps, const float* ssq, int64_t ld_ssq, void* stream) {
     if (!x || !y || !ssq) return fail(FLITE_ERR_INVALID, "rmsnorm_ssq: null pointer");
-    if (d % 128 || ldx % 8 || ldy % 8 || ld_ssq < d / 128) return fail(FLITE_ERR_INVALID, "rmsnorm_ssq: d must be a multiple of 128, ld of 8");
+    if (d % 64 || ldx % 8 || ldy % 8 || ld_ssq < d / 64) return fail(FLITE_ERR_INVALID, "rmsnorm_ssq: d must be a multiple of 64, ld of 8, ld_ssq >= d / 64");
     if (weight_mode != 0 && !w) return fail(FLITE_ERR_INVALID, "rmsnorm_ssq: weight_mode %d needs a weight", weight_mode);
     if ((scale == nullptr) != (shift == nullptr)) return fail(FLITE_ERR_INVALID, "rmsnorm_ssq: scale and shift go together");
     if (rows <= 0) return 0;

@@ -193,6 +193,8 @@ class DiT(nn.Module):
         self.attn_streamk = os.environ.get("FLITE_ATTN_STREAMK", "0")
         # gated-residual GEMM epilogues emit per-row sum-of-squares slots, the RMSNorm after them is single-pass
         self.fused_norm_stats = os.environ.get("FLITE_FUSED_NORM_STATS", "1") != "0"
+        # ... and the GEMM unit that completes a block of rows normalises + modulates them for the next GEMM itself
+        self.fused_norm = os.environ.get("FLITE_FUSED_NORM", "1") != "0"
         self.gemm_variant = GEMM_AUTO
         self.sp_group = None      # Ulysses sequence-parallel process group (see enable_sequence_parallel)
         self.sp_fused = False     # exchanges fused into the kernels over NVLink peer memory instead of NCCL
@@ -473,6 +475,7 @@ class DiT(nn.Module):
         fmod = ops.gemm(st, fm.weight, fm.bias, variant=v)                   # [B, 2d]
         (shift_sa, scale_sa, gate_sa, shift_ca, scale_ca, gate_ca, shift_mlp, scale_mlp, gate_mlp) = (
             mod[:, k * d:(k + 1) * d] for k in range(9))
+        fshift, fscale = fmod[:, :d], fmod[:, d:]
 
         nbuf = self._buf("n", (T, d), dev)
         abuf = self._buf("attn", (T, d), dev)
@@ -480,6 +483,22 @@ class DiT(nn.Module):
         # epilogue and consumed by the single-pass RMSNorm that follows it (FLITE_FUSED_NORM_STATS=0: two-pass norm)
         ssq = self._ssq_buf(T, d, dev) if (self.fused_norm_stats and d % 128 == 0) else None
         ssq_ok = False          # the slots describe the current xs (false until the first gated-residual GEMM has run)
+        # ... and the GEMM unit that completes a block of rows also normalises + modulates them for the NEXT consumer
+        # (straight into nbuf, rows still in L2), so the 2 - 3 norm launches per block disappear (FLITE_FUSED_NORM=0: off)
+        fuse_norm = ssq is not None and self.fused_norm
+        if fuse_norm:
+            cnt = self._ws.get(("nf_counters", T))
+            if cnt is None or cnt.device != dev:
+                cnt = torch.zeros(2 * ((T + 127) // 128), dtype=torch.int32, device=dev)
+                self._ws[("nf_counters", T)] = cnt
+
+        def next_norm(weight, mode, sc, sh):
+            if not fuse_norm:
+                return None
+            return dict(out=nbuf, weight=weight, weight_mode=mode, scale=sc, shift=sh, counters=cnt)
+
+        n_ready = False         # nbuf already holds the normalised + modulated input of the next GEMM
+        fw = self.final_norm.weight
         qc = self._buf("qc", (T, d), dev)
         inter = self.blocks[0].mlp.gate_proj.weight.shape[0] if len(self.blocks) else 0
         hmid = self._buf("hmid", (T, inter), dev)
@@ -511,9 +530,13 @@ class DiT(nn.Module):
         x_variant = ATTN_XRES if (ctx.Lc <= 256 and ops.get_tuning(12) == ATTN_XRES) else 0
         for i, blk in enumerate(self.blocks):
             # ---- self-attention (model.py:283-289)
-            ops.rmsnorm_modulate(xs, blk.norm1.weight, 1, scale_sa, shift_sa, rows_per_sample=Lq, out=nbuf,
-                                 ssq=ssq if ssq_ok else None)
+            if not n_ready:
+                ops.rmsnorm_modulate(xs, blk.norm1.weight, 1, scale_sa, shift_sa, rows_per_sample=Lq, out=nbuf,
+                                     ssq=ssq if ssq_ok else None)
             sa = blk.self_attn
+            # what follows the self-attention residual: norm2 (cross-attention blocks) or norm3
+            nn_sa = (next_norm(blk.norm2.weight, 1, scale_ca, shift_ca) if blk.cross_attn is not None
+                     else next_norm(blk.norm3.weight, 1, scale_mlp, shift_mlp))
             if sp is None:
                 ops.gemm(nbuf, sa.qkv.weight, sa.qkv.bias, epilogue=EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin,
                          qk_cols=2 * d, rows_per_sample=Lq, variant=v, out=qkv)
@@ -534,7 +557,7 @@ class DiT(nn.Module):
                                              cu_full, hq, L, scale, ao_tab, P, Lq, rk * hq, d)
                 sym.exchange_done(stream)
                 ops.gemm(p2p_ao, sa.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_sa,
-                         rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq)
+                         rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq, norm=nn_sa)
             else:
                 # Ulysses: the QKV epilogue scatters heads into the all-to-all send layout; after the exchange this
                 # rank holds q|k|v of its hq heads for the FULL sequence; the second exchange returns the outputs.
@@ -556,31 +579,41 @@ class DiT(nn.Module):
                     ops.permute_021(ao_recv[b].view(P, Lq, dq), out=abuf[b * Lq:(b + 1) * Lq].view(Lq, P, dq))
             if not (sp is not None and self.sp_fused):
                 ops.gemm(abuf, sa.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_sa,
-                         rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq)
+                         rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq, norm=nn_sa)
             ssq_ok = ssq is not None
+            n_ready = nn_sa is not None
             # ---- cross-attention (model.py:291-297): token-local, context K/V replicated
             if blk.cross_attn is not None:
                 ca = blk.cross_attn
-                ops.rmsnorm_modulate(xs, blk.norm2.weight, 1, scale_ca, shift_ca, rows_per_sample=Lq, out=nbuf,
-                                     ssq=ssq if ssq_ok else None)
+                if not n_ready:
+                    ops.rmsnorm_modulate(xs, blk.norm2.weight, 1, scale_ca, shift_ca, rows_per_sample=Lq, out=nbuf,
+                                         ssq=ssq if ssq_ok else None)
                 ops.gemm(nbuf, ca.q.weight, ca.q.bias, epilogue=EPI_QKV_ROPE, qk_cols=d, rows_per_sample=Lq,
                          variant=v, out=qc)
                 ck, cv = ctx.kvs[i]
                 ops.attention_varlen(qc, ck, cv, cu_x, ctx.cu_k, nh, Lq, scale, out=abuf, variant=x_variant)
+                nn_ca = next_norm(blk.norm3.weight, 1, scale_mlp, shift_mlp)
                 ops.gemm(abuf, ca.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_ca,
-                         rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq)
+                         rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq, norm=nn_ca)
+                n_ready = nn_ca is not None
             # ---- SwiGLU MLP (model.py:299-301)
-            ops.rmsnorm_modulate(xs, blk.norm3.weight, 1, scale_mlp, shift_mlp, rows_per_sample=Lq, out=nbuf,
-                                 ssq=ssq if ssq_ok else None)
+            if not n_ready:
+                ops.rmsnorm_modulate(xs, blk.norm3.weight, 1, scale_mlp, shift_mlp, rows_per_sample=Lq, out=nbuf,
+                                     ssq=ssq if ssq_ok else None)
             ops.gemm(nbuf, self._gate_up(i, blk), None, epilogue=EPI_SWIGLU, variant=v, out=hmid)
+            # what follows the MLP residual: the next block's norm1, or the final norm + final modulation
+            if i + 1 < len(self.blocks):
+                nn_mlp = next_norm(self.blocks[i + 1].norm1.weight, 1, scale_sa, shift_sa)
+            else:
+                nn_mlp = next_norm(fw, 2 if fw is not None else 0, fscale, fshift)
             ops.gemm(hmid, blk.mlp.down_proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_mlp,
-                     rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq)
+                     rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq, norm=nn_mlp)
+            n_ready = nn_mlp is not None
 
         # ---- final head (model.py:577-590)
-        fshift, fscale = fmod[:, :d], fmod[:, d:]
-        fw = self.final_norm.weight
-        ops.rmsnorm_modulate(xs, fw, 2 if fw is not None else 0, fscale, fshift, rows_per_sample=Lq, out=nbuf,
-                             ssq=ssq if ssq_ok else None)
+        if not n_ready:
+            ops.rmsnorm_modulate(xs, fw, 2 if fw is not None else 0, fscale, fshift, rows_per_sample=Lq, out=nbuf,
+                                 ssq=ssq if ssq_ok else None)
         o = ops.gemm(nbuf, self.final_proj.weight, self.final_proj.bias, variant=v)
         if sp is not None:
             # gather every rank's token slice: [rank][sample][Lq*64] -> [sample][rank][Lq*64] = [B*L, 64]

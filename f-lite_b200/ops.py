@@ -313,10 +313,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          epilogue: int = EPI_STORE, resid: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
          rows_per_sample: int = 0, rope_cos: Optional[torch.Tensor] = None, rope_sin: Optional[torch.Tensor] = None,
          qk_cols: int = 0, eps: float = 1e-6, variant: int = GEMM_AUTO, out: Optional[torch.Tensor] = None,
-         sp_ranks: int = 0, sp_heads_per_rank: int = 0, ssq_out: Optional[torch.Tensor] = None):
+         sp_ranks: int = 0, sp_heads_per_rank: int = 0, ssq_out: Optional[torch.Tensor] = None,
+         norm: Optional[dict] = None):
     """out = epilogue(a @ w.T); a [M, K], w [N, K] (nn.Linear layout), bf16.
-    ``ssq_out`` [M, >= N/128] fp32 (EPI_GATED_RES only): also emit the per-row sum of squares of the stored rows, one slot
-    per 128 columns, for the single-pass ``rmsnorm_modulate(..., ssq=)`` that follows."""
+    ``ssq_out`` [M, >= N/64] fp32 (EPI_GATED_RES only): also emit the per-row sum of squares of the stored rows, one slot
+    per 64 columns, for the single-pass ``rmsnorm_modulate(..., ssq=)`` that follows.
+    ``norm`` (with ``ssq_out``): ``dict(out=, weight=, weight_mode=, scale=, shift=, counters=)`` -- the GEMM unit that
+    completes a block of rows also writes ``norm_w(x') * (1 + scale) + shift`` for them into ``out`` (the RMSNorm + adaLN
+    modulate that follows the residual update in the reference, model.py:283-301), so no norm launch is needed."""
     lib = _lib.load()
     _chk(a, "a")
     _chk(w, "w")
@@ -343,6 +347,20 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         if epilogue != EPI_GATED_RES:
             raise _lib.FliteError("gemm: ssq_out goes with the gated-residual epilogue")
         _chk(ssq_out, "ssq_out", torch.float32)
+        if norm is not None:
+            n_out, n_w, n_sc, n_sh = norm["out"], norm.get("weight"), norm.get("scale"), norm.get("shift")
+            _chk(n_out, "norm.out")
+            _chk(norm["counters"], "norm.counters", torch.int32)
+            _lib.check(lib.flite_gemm_gated_res_norm(
+                a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), M, N, K, _ptr(bias),
+                resid.data_ptr(), resid.stride(0), gate.data_ptr(), gate.stride(0), rows_per_sample, ssq_out.data_ptr(),
+                ssq_out.stride(0), n_out.data_ptr(), n_out.stride(0), _ptr(n_w), int(norm.get("weight_mode", 1)), _ptr(n_sc),
+                _ptr(n_sh), n_sc.stride(0) if n_sc is not None else 0, float(eps), norm["counters"].data_ptr(), variant,
+                _stream()), "gemm_gated_res_norm")
+            LAUNCHES[0] += 1
+            if hook is not None:
+                hook("gemm", "end", (M, N, K, epilogue))
+            return out
         _lib.check(lib.flite_gemm_gated_res_ssq(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                                 out.stride(0), M, N, K, _ptr(bias), resid.data_ptr(), resid.stride(0),
                                                 gate.data_ptr(), gate.stride(0), rows_per_sample, ssq_out.data_ptr(),

@@ -235,3 +235,25 @@ def test_encode_prompt_contract_with_stand_in_encoder():
     assert e2.shape[0] == 1 and n2.shape[0] == 1 and m2.dtype == torch.long and nm2.sum() > 0
     assert not torch.equal(n2, torch.zeros_like(n2))                    # a real negative prompt is encoded, not zeros
     assert "<user>blurry" in proc.calls[-1]["text"][0] and "<user>a red fox" in proc.calls[-2]["text"][0]
+
+
+def test_custom_op_registrations_and_fake_shapes():
+    """the hot entry points are also registered with torch.library.custom_op (opaque operators with
+    fake / meta implementations and declared mutations) for callers that live in a torch graph."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    from flite_b200 import custom_ops
+    for name in custom_ops.REGISTERED:
+        assert hasattr(torch.ops.flite_b200, name), name
+    with FakeTensorMode():
+        a = torch.empty(5, 64, dtype=torch.bfloat16, device="cuda")
+        w = torch.empty(128, 64, dtype=torch.bfloat16, device="cuda")
+        assert tuple(torch.ops.flite_b200.linear(a, w, None).shape) == (5, 128)
+        q = torch.empty(40, 512, dtype=torch.bfloat16, device="cuda")
+        cu = torch.empty(3, dtype=torch.int32, device="cuda")
+        assert tuple(torch.ops.flite_b200.attention_varlen(q, q, q, cu, cu, 2, 20, 0.0625).shape) == (40, 512)
+        x = torch.empty(7, 256, dtype=torch.bfloat16, device="cuda")
+        assert tuple(torch.ops.flite_b200.rmsnorm_modulate(x, x[0], x[:1], x[:1], 7).shape) == (7, 256)
+    schema = str(torch.ops.flite_b200.cfg_euler_.default._schema)
+    assert "Tensor(a0!) acc" in schema and "lat_out" in schema            # in-place arguments are declared as mutated

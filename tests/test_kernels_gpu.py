@@ -724,3 +724,18 @@ def test_gated_residual_gemm_emits_ssq_slots_for_single_pass_rmsnorm(M, d, K):
     assert (one == two).float().mean().item() > 0.999 and rel(one, two) <= 2e-4
     one2 = ops.rmsnorm_modulate(x, nw, 2, ssq=ssq)
     assert rel(one2, ops.rmsnorm_modulate(x, nw, 2)) <= 2e-4
+    # flite_gemm_gated_res_norm: the GEMM unit that completes a block of rows normalises them itself -- same bits as the
+    # GEMM followed by the single-pass norm, twice in a row (the completion counters reset themselves)
+    cnt = torch.zeros(2 * ((M + 127) // 128), dtype=torch.int32, device=DEV)
+    for wmode, sc, sh in ((1, mod[:, :d], mod[:, d:]), (2, None, None), (0, mod[:, :d], mod[:, d:])):
+        want = ops.rmsnorm_modulate(x, nw if wmode else None, wmode, sc, sh, rows_per_sample=rps, ssq=ssq)
+        for _ in range(2):
+            x2 = x0.clone()
+            ssq2 = torch.full_like(ssq, -1.0)
+            fused = torch.full((M + 4, d), 7.0, dtype=torch.bfloat16, device=DEV)
+            ops.gemm(a, w, None, epilogue=ops.EPI_GATED_RES, resid=x2, gate=gate, rows_per_sample=rps, out=x2, ssq_out=ssq2,
+                     norm=dict(out=fused[:M], weight=nw if wmode else None, weight_mode=wmode, scale=sc, shift=sh,
+                               counters=cnt))
+            assert torch.equal(x2, plain) and torch.equal(ssq2, ssq)
+            assert torch.equal(fused[:M], want), f"fused norm differs (weight_mode {wmode})"
+            assert bool((fused[M:] == 7.0).all()) and int(cnt.abs().sum().item()) == 0

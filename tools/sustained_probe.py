@@ -41,39 +41,7 @@ KERNELS = {
     "attention stream-K 2x12x4112^2": (lambda: ops.attention_streamk(qkv_in[:, :d], qkv_in[:, d:2 * d], qkv_in[:, 2 * d:], cu, cu, 12, T // 2, T // 2, 256 ** -0.5, out=o_at), 4.0 * 2 * 12 * (T // 2) ** 2 * 256),
     "rmsnorm_modulate two-pass 8224x3072": (lambda: ops.rmsnorm_modulate(x, nw, 1, mod[:, :d], mod[:, d:], rows_per_sample=T // 2, out=nrm), 0.0),
 }
-Q = "clocks.sm,power.draw"
-
-
-def sample_loop(fn, seconds):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    proc = subprocess.Popen(["nvidia-smi", "-i", "0", f"--query-gpu={Q}", "--format=csv,noheader,nounits", "-lms", "50"],
-                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 0
-    t0 = time.time()
-    e0.record()
-    while time.time() - t0 < seconds:
-        for _ in range(20):
-            fn()
-        n += 20
-        torch.cuda.synchronize()
-    e1.record()
-    torch.cuda.synchronize()
-    proc.terminate()
-    out, _ = proc.communicate(timeout=5)
-    ms = e0.elapsed_time(e1) / n
-    clk, pw = [], []
-    for line in out.strip().splitlines()[len(out.strip().splitlines()) // 2:]:      # second half: steady state
-        f = [v.strip() for v in line.split(",")]
-        try:
-            clk.append(float(f[0])); pw.append(float(f[1]))
-        except Exception:
-            pass
-    clk.sort(); pw.sort()
-    return ms, (clk[len(clk) // 2] if clk else None), (pw[len(pw) // 2] if pw else None)
-
+from tools.sustained_probe_lib import sample_loop
 
 res = {}
 for name, (fn, flops) in KERNELS.items():
