@@ -244,10 +244,10 @@ class DiT(nn.Module):
         return self._sp_sym[1:]
 
     def _ssq_buf(self, T, d, device):
-        key = ("ssq", T, d // 128)
+        key = ("ssq", T, d // 64)
         b = self._ws.get(key)
         if b is None or b.device != device:
-            b = torch.empty((T, d // 128), dtype=torch.float32, device=device)
+            b = torch.empty((T, d // 64), dtype=torch.float32, device=device)      # one slot per 64 columns
             self._ws[key] = b
         return b
 
@@ -479,7 +479,7 @@ class DiT(nn.Module):
 
         nbuf = self._buf("n", (T, d), dev)
         abuf = self._buf("attn", (T, d), dev)
-        # per-row sum-of-squares slots of the residual stream (one per 128 columns), written by every gated-residual GEMM
+        # per-row sum-of-squares slots of the residual stream (one per 64 columns), written by every gated-residual GEMM
         # epilogue and consumed by the single-pass RMSNorm that follows it (FLITE_FUSED_NORM_STATS=0: two-pass norm)
         ssq = self._ssq_buf(T, d, dev) if (self.fused_norm_stats and d % 128 == 0) else None
         ssq_ok = False          # the slots describe the current xs (false until the first gated-residual GEMM has run)

@@ -171,7 +171,7 @@ def rmsnorm_modulate(x: torch.Tensor, weight: Optional[torch.Tensor], weight_mod
                      rows_per_sample: int = 0, eps: float = 1e-6, out: Optional[torch.Tensor] = None,
                      ssq: Optional[torch.Tensor] = None):
     """x [rows, d]; scale/shift are [B, d] views into the modulation matrix (same row stride).
-    ``ssq`` [rows, >= d/128] fp32: per-row sum-of-squares slots written by the gated-residual GEMM that produced ``x``
+    ``ssq`` [rows, >= d/64] fp32: per-row sum-of-squares slots written by the gated-residual GEMM that produced ``x``
     (``gemm(..., ssq_out=)``): the single-pass kernel, which does not reduce the row itself."""
     lib = _lib.load()
     _chk(x, "x")

@@ -696,7 +696,7 @@ def test_attention_streamk_rejects_ragged_lengths():
 
 @pytest.mark.parametrize("M,d,K", [(8224, 3072, 3072), (300, 512, 1024), (4100, 1024, 512), (96, 512, 512)])
 def test_gated_residual_gemm_emits_ssq_slots_for_single_pass_rmsnorm(M, d, K):
-    """flite_gemm_gated_res_ssq + flite_rmsnorm_modulate_ssq: the epilogue's per-row, per-128-column sum-of-squares slots
+    """flite_gemm_gated_res_ssq + flite_rmsnorm_modulate_ssq: the epilogue's per-row, per-64-column sum-of-squares slots
     equal the sums recomputed from the rows it stored, the GEMM output is bit-identical to the plain gated-residual GEMM,
     and the single-pass norm agrees with the two-pass kernel (same rounding points; only the fp32 summation order of
     sum(x^2) differs => rare 1-ulp flips)."""
@@ -711,10 +711,10 @@ def test_gated_residual_gemm_emits_ssq_slots_for_single_pass_rmsnorm(M, d, K):
     plain = x0.clone()
     ops.gemm(a, w, None, epilogue=ops.EPI_GATED_RES, resid=plain, gate=gate, rows_per_sample=rps, out=plain)
     x = x0.clone()
-    ssq = torch.full((M, d // 128), -1.0, dtype=torch.float32, device=DEV)
+    ssq = torch.full((M, d // 64), -1.0, dtype=torch.float32, device=DEV)
     ops.gemm(a, w, None, epilogue=ops.EPI_GATED_RES, resid=x, gate=gate, rows_per_sample=rps, out=x, ssq_out=ssq)
     assert torch.equal(x, plain)
-    ref = x.float().pow(2).view(M, d // 128, 128).sum(-1)
+    ref = x.float().pow(2).view(M, d // 64, 64).sum(-1)
     assert bool((ssq >= 0).all())
     assert ((ssq - ref).abs() / ref.clamp_min(1e-6)).max().item() <= 1e-5
     nw = (1 + 0.1 * torch.randn(d, device=DEV, generator=g)).bfloat16()
