@@ -168,7 +168,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     // (a half-width unit is shared by the two epilogue warpgroups in 32-column chunks => >= 64 columns; SwiGLU needs whole
     // 128-column [gate | up] groups)
     const bool can_split = kEpi != EPI_QKV_ROPE && (BLOCK_N / 2) % (kEpi == EPI_SWIGLU ? 128 : 64) == 0 &&
-                           (BLOCK_N / 2 / kCtaGroup) >= 8 && g_tuning[FLITE_TUNE_GEMM_TAIL_SPLIT] == 0;
+                           (BLOCK_N / 2 / kCtaGroup) >= 8 && g_tuning[FLITE_TUNE_GEMM_TAIL_SPLIT] == 0 &&
+                           (p.ssq_out == nullptr || (BLOCK_N / 2) % 128 == 0);   // a thread must own whole 64-column ssq slots
     const int tail = num_tiles % max_clusters;
     if (can_split && tail > 0 && 2 * tail <= max_clusters) {
         p.full_units = num_tiles - tail;
@@ -247,6 +248,14 @@ extern "C" {
 
 int flite_abi_version(void) { return FLITE_ABI_VERSION; }
 const char* flite_last_error(void) { return g_err; }
+
+int flite_debug_nf_read(unsigned long long* out4) {   // experiments: read and clear the fused-norm job timers
+    unsigned long long z[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out4, g_nf_dbg, sizeof(z)));
+    CUDA_TRY(cudaMemcpyToSymbol(g_nf_dbg, z, sizeof(z)));
+    return 0;
+}
 
 int flite_set_tuning(int key, int value) {
     if (key < 0 || key >= 32) return fail(FLITE_ERR_INVALID, "set_tuning: unknown key %d", key);
@@ -607,6 +616,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
         p.nf_w = (const __nv_bfloat16*)nf->w; p.nf_wmode = nf->wmode;
         p.nf_scale = (const __nv_bfloat16*)nf->scale; p.nf_shift = (const __nv_bfloat16*)nf->shift; p.nf_ld_mod = nf->ld_mod;
         p.nf_counters = nf->counters;
+        p.nf_debug = g_tuning[15];      // FLITE_TUNE_NF_DEBUG (experiments)
     }
     p.stage_stores = (epilogue == EPI_QKV_ROPE && (peers != nullptr || g_tuning[FLITE_TUNE_QKV_STAGED_STORES])) ? 1 : 0;
 

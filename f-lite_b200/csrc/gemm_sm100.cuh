@@ -86,10 +86,13 @@ struct GemmParams {
     const __nv_bfloat16* nf_shift;
     long long nf_ld_mod;
     unsigned int* nf_counters;
+    int nf_debug;                // profiling experiments only: bit0 skip the norm job, bit1 skip the per-thread fence
     // L2 eviction-priority hints of the A / W tile loads (0 = plain load); chosen with the band height so that the operand
     // the rasterisation keeps resident is evict_last and the one that streams past it is evict_first.
     unsigned long long hint_a, hint_b;
 };
+
+__device__ unsigned long long g_nf_dbg[4];   // experiments: [0] max job ns, [1] sum job ns, [2] jobs, [3] units
 
 FLITE_DEVICE void norm_finished_rows(const GemmParams& p, int row0, int nrows, int warp, int lane) {
     constexpr int MAXC = 12;                       // 16-byte chunks per lane and pass (d = 3072 in one pass)
@@ -455,7 +458,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     // chain) normalises those rows right away -- while they are still in L2 and while the MMA warp
                     // runs the next tile -- and resets the counter for the next launch.
                     unsigned int* flag = reinterpret_cast<unsigned int*>(smem + S::BAR_OFFSET + 192);
-                    __threadfence();
+                    if (!(p.nf_debug & 2)) __threadfence();
                     named_bar_sync(5, 256);
                     if (threadIdx.x == 64) {
                         unsigned int* cnt = p.nf_counters + (m_blk * 2 + (int)cta_rank);
@@ -469,9 +472,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         *flag = last ? 1u : 0u;
                     }
                     named_bar_sync(5, 256);
-                    if (*flag != 0u) {
+                    if ((p.nf_debug & 4) && threadIdx.x == 64) atomicAdd(&g_nf_dbg[3], 1ull);
+                    if (*flag != 0u && !(p.nf_debug & 1)) {
                         const int rows_here = narrow ? 64 : 128;
+                        const uint64_t t0 = (p.nf_debug & 4) ? globaltimer_ns() : 0;
                         norm_finished_rows(p, m0, rows_here, (warp_idx - 2), lane);
+                        if (p.nf_debug & 4) {
+                            named_bar_sync(5, 256);
+                            if (threadIdx.x == 64) {
+                                const unsigned long long dt = globaltimer_ns() - t0;
+                                atomicMax(&g_nf_dbg[0], dt);
+                                atomicAdd(&g_nf_dbg[1], dt);
+                                atomicAdd(&g_nf_dbg[2], 1ull);
+                            }
+                        }
                     }
                 }
                 continue;   // barrier already signalled
