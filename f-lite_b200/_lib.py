@@ -41,10 +41,6 @@ SIGNATURES = {
     "flite_pack_context": [_P, _L, _P, _L, _P, _I, _I, _I, _P, _P, _P, _P],
     "flite_gemm_bf16": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _I, _I, _P, _L, _P, _L, _I, _P, _P, _I, _F,
                         _I, _I, _I, _P],
-    "flite_gemm_gated_res_ssq": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _P, _L, _I, _P, _L, _I, _P],
-    "flite_gemm_gated_res_norm": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _P, _L, _I, _P, _L, _P, _L, _P, _I, _P, _P, _L,
-                                  _F, _P, _I, _P],
-    "flite_rmsnorm_modulate_ssq": [_P, _L, _P, _L, _P, _I, _P, _P, _L, _I, _I, _I, _F, _P, _L, _P],
     "flite_attention_varlen": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _I, _F, _I, _P],
     "flite_attention_streamk_workspace_bytes": [],
     "flite_attention_streamk": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P, _L, _P],

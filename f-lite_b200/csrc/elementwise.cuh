@@ -97,38 +97,6 @@ rmsnorm_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv
     }
 }
 
-// Single-pass variant: the sum of squares of every row arrives pre-reduced in d / 64 fp32 slots written by the
-// gated-residual GEMM epilogue that produced x (GemmParams::ssq_out), so the row is read ONCE: the 16-byte loads feed
-// the normalise / modulate / store chain directly, with no reduction and no second pass in between.  The slots are
-// summed in a fixed order (lane i takes slot i, xor-shuffle tree), i.e. the result does not depend on the launch shape.
-__global__ void __launch_bounds__(128)
-rmsnorm_modulate_ssq_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
-                            long long ldy, const __nv_bfloat16* __restrict__ w, int weight_mode,
-                            const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift,
-                            long long ld_mod, int rows_per_sample, int rows, int d, float eps,
-                            const float* __restrict__ ssq, long long ld_ssq) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const int lane = threadIdx.x & 31;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
-    const int nchunk = d >> 3, nslot = d >> 6;
-    float part = 0.f;
-    for (int i = lane; i < nslot; i += 32) part += __ldcg(ssq + (long long)row * ld_ssq + i);
-    const float rstd = rsqrtf(warp_sum(part) / (float)d + eps);
-    const bool mod = scale != nullptr;
-    const long long s = (long long)(row / rows_per_sample) * ld_mod;
-    uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int c = lane; c < nchunk; c += 32) {
-        const uint4 wv = weight_mode != 0 ? __ldg(reinterpret_cast<const uint4*>(w) + c) : z;
-        const uint4 scv = mod ? __ldg(reinterpret_cast<const uint4*>(scale + s) + c) : z;
-        const uint4 shv = mod ? __ldg(reinterpret_cast<const uint4*>(shift + s) + c) : z;
-        yr[c] = norm_mod_chunk(__ldcg(xr + c), rstd, wv, weight_mode, mod, scv, shv);
-    }
-}
-
 // Register-resident variant for d <= 8 * 32 * MAXC: the whole row is loaded once (MAXC independent 16-byte
 // loads in flight per lane), reduced, normalised and written -- one HBM read + one write per element.
 template <int MAXC>

@@ -165,11 +165,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     // one wave (needs 128-column granularity for SwiGLU pairs, whole heads for the QKV epilogue => not there)
     p.full_units = num_tiles;
     p.num_units = num_tiles;
-    // (a half-width unit is shared by the two epilogue warpgroups in 32-column chunks => >= 64 columns; SwiGLU needs whole
-    // 128-column [gate | up] groups)
-    const bool can_split = kEpi != EPI_QKV_ROPE && (BLOCK_N / 2) % (kEpi == EPI_SWIGLU ? 128 : 64) == 0 &&
-                           (BLOCK_N / 2 / kCtaGroup) >= 8 && g_tuning[FLITE_TUNE_GEMM_TAIL_SPLIT] == 0 &&
-                           (p.ssq_out == nullptr || (BLOCK_N / 2) % 128 == 0);   // a thread must own whole 64-column ssq slots
+    const bool can_split = kEpi != EPI_QKV_ROPE && (BLOCK_N / 2) % (kEpi == EPI_SWIGLU ? 128 : 32) == 0 &&
+                           (BLOCK_N / 2 / kCtaGroup) >= 8 && g_tuning[FLITE_TUNE_GEMM_TAIL_SPLIT] == 0;
     const int tail = num_tiles % max_clusters;
     if (can_split && tail > 0 && 2 * tail <= max_clusters) {
         p.full_units = num_tiles - tail;
@@ -248,14 +245,6 @@ extern "C" {
 
 int flite_abi_version(void) { return FLITE_ABI_VERSION; }
 const char* flite_last_error(void) { return g_err; }
-
-int flite_debug_nf_read(unsigned long long* out4) {   // experiments: read and clear the fused-norm job timers
-    unsigned long long z[4] = {0, 0, 0, 0};
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpyFromSymbol(out4, g_nf_dbg, sizeof(z)));
-    CUDA_TRY(cudaMemcpyToSymbol(g_nf_dbg, z, sizeof(z)));
-    return 0;
-}
 
 int flite_set_tuning(int key, int value) {
     if (key < 0 || key >= 32) return fail(FLITE_ERR_INVALID, "set_tuning: unknown key %d", key);
@@ -518,28 +507,11 @@ struct SpPeers {
     int seq_len;
 };
 
-struct NormFuse {          // fused RMSNorm + modulate of the finished rows (GemmParams::nf_*)
-    void* out;
-    int64_t ldo;
-    const void* w;
-    int wmode;
-    const void* scale;
-    const void* shift;
-    int64_t ld_mod;
-    unsigned int* counters;
-};
-
 static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
                      const void* bias, int act, int epilogue, const void* resid, int64_t ldr, const void* gate,
                      int64_t ld_gate, int rows_per_sample, const void* rope_cos, const void* rope_sin, int qk_cols,
-                     float eps, int sp_ranks, int sp_heads_per_rank, int variant, void* stream, const SpPeers* peers,
-                     float* ssq_out = nullptr, int64_t ssq_ld = 0, const NormFuse* nf = nullptr) {
+                     float eps, int sp_ranks, int sp_heads_per_rank, int variant, void* stream, const SpPeers* peers) {
     if (!A || !W || !C) return fail(FLITE_ERR_INVALID, "gemm: null pointer");
-    if (ssq_out && (epilogue != EPI_GATED_RES || N % 64 || ssq_ld < N / 64))
-        return fail(FLITE_ERR_INVALID, "gemm: ssq_out needs the gated-residual epilogue, N %% 64 == 0 and ssq_ld >= N / 64");
-    if (nf && (!ssq_out || !nf->out || !nf->counters || nf->ldo % 8 || (nf->wmode != 0 && !nf->w) ||
-               (nf->scale == nullptr) != (nf->shift == nullptr) || nf->ld_mod % 8 || C == nf->out))
-        return fail(FLITE_ERR_INVALID, "gemm: fused norm needs ssq_out, an output buffer distinct from C, counters, and scale/shift together");
     if (M <= 0) return 0;
     if (K <= 0 || K % 64) return fail(FLITE_ERR_INVALID, "gemm: K = %d must be a positive multiple of 64", K);
     if (N <= 0 || N % 64) return fail(FLITE_ERR_INVALID, "gemm: N = %d must be a positive multiple of 64", N);
@@ -608,16 +580,6 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
         p.sp_rank = peers->rank;
         p.sp_seq = peers->seq_len;
     }
-    p.ssq_out = ssq_out; p.ssq_ld = ssq_ld;
-    if (ssq_out && variant != FLITE_GEMM_2CTA_N256 && variant != FLITE_GEMM_1CTA_N256 && variant != FLITE_GEMM_1CTA_N128)
-        return fail(FLITE_ERR_INVALID, "gemm: ssq_out needs an N-tile that is a multiple of 128 columns");
-    if (nf) {
-        p.nf_out = (__nv_bfloat16*)nf->out; p.nf_ldo = nf->ldo;
-        p.nf_w = (const __nv_bfloat16*)nf->w; p.nf_wmode = nf->wmode;
-        p.nf_scale = (const __nv_bfloat16*)nf->scale; p.nf_shift = (const __nv_bfloat16*)nf->shift; p.nf_ld_mod = nf->ld_mod;
-        p.nf_counters = nf->counters;
-        p.nf_debug = g_tuning[15];      // FLITE_TUNE_NF_DEBUG (experiments)
-    }
     p.stage_stores = (epilogue == EPI_QKV_ROPE && (peers != nullptr || g_tuning[FLITE_TUNE_QKV_STAGED_STORES])) ? 1 : 0;
 
     CUtensorMap ta, tb, tbh, tah;
@@ -645,48 +607,6 @@ int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
                     float eps, int sp_ranks, int sp_heads_per_rank, int variant, void* stream) {
     return gemm_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, act, epilogue, resid, ldr, gate, ld_gate, rows_per_sample,
                      rope_cos, rope_sin, qk_cols, eps, sp_ranks, sp_heads_per_rank, variant, stream, nullptr);
-}
-
-int flite_gemm_gated_res_ssq(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
-                             const void* bias, const void* resid, int64_t ldr, const void* gate, int64_t ld_gate,
-                             int rows_per_sample, float* ssq_out, int64_t ssq_ld, int variant, void* stream) {
-    if (!ssq_out) return fail(FLITE_ERR_INVALID, "gemm_gated_res_ssq: null ssq_out");
-    return gemm_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, 0, EPI_GATED_RES, resid, ldr, gate, ld_gate, rows_per_sample,
-                     nullptr, nullptr, 0, 1e-6f, 0, 0, variant, stream, nullptr, ssq_out, ssq_ld);
-}
-
-int flite_gemm_gated_res_norm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
-                              const void* bias, const void* resid, int64_t ldr, const void* gate, int64_t ld_gate,
-                              int rows_per_sample, float* ssq_out, int64_t ssq_ld, void* norm_out, int64_t ld_norm_out,
-                              const void* norm_w, int weight_mode, const void* scale, const void* shift, int64_t ld_mod,
-                              float eps, unsigned int* counters, int variant, void* stream) {
-    if (!ssq_out || !norm_out || !counters) return fail(FLITE_ERR_INVALID, "gemm_gated_res_norm: null pointer");
-    NormFuse nf{norm_out, ld_norm_out, norm_w, weight_mode, scale, shift, ld_mod, counters};
-    return gemm_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, 0, EPI_GATED_RES, resid, ldr, gate, ld_gate, rows_per_sample,
-                     nullptr, nullptr, 0, eps, 0, 0, variant, stream, nullptr, ssq_out, ssq_ld, &nf);
-}
-
-int flite_rmsnorm_modulate_ssq(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w, int weight_mode,
-                               const void* scale, const void* shift, int64_t ld_mod, int rows_per_sample, int rows, int d,
-                               float eps, const float* ssq, int64_t ld_ssq, void* stream) {
-    if (!x || !y || !ssq) return fail(FLITE_ERR_INVALID, "rmsnorm_ssq: null pointer");
-    if (d % 64 || ldx % 8 || ldy % 8 || ld_ssq < d / 64) return fail(FLITE_ERR_INVALID, "rmsnorm_ssq: d must be a multiple of 64, ld of 8, ld_ssq >= d / 64");
-    if (weight_mode != 0 && !w) return fail(FLITE_ERR_INVALID, "rmsnorm_ssq: weight_mode %d needs a weight", weight_mode);
-    if ((scale == nullptr) != (shift == nullptr)) return fail(FLITE_ERR_INVALID, "rmsnorm_ssq: scale and shift go together");
-    if (rows <= 0) return 0;
-    if (rows_per_sample <= 0) rows_per_sample = rows;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((rows + 3) / 4);
-    cfg.blockDim = dim3(128);
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[2];
-    cfg.attrs = attr;
-    cfg.numAttrs = fill_launch_attrs(attr, 0);
-    const long long ldx_ = ldx, ldy_ = ldy, ld_mod_ = ld_mod, ld_ssq_ = ld_ssq;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, rmsnorm_modulate_ssq_kernel, (const __nv_bfloat16*)x, ldx_, (__nv_bfloat16*)y, ldy_,
-                                (const __nv_bfloat16*)w, weight_mode, (const __nv_bfloat16*)scale, (const __nv_bfloat16*)shift,
-                                ld_mod_, rows_per_sample, rows, d, eps, ssq, ld_ssq_));
-    return 0;
 }
 
 int flite_gemm_qkv_p2p(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, const void* bias,

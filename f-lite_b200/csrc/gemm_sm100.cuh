@@ -17,7 +17,6 @@
 #pragma once
 
 #include "common.cuh"
-#include "elementwise.cuh"   // norm_mod_chunk / warp_sum: the fused "norm of finished rows" uses the norm kernels' math
 
 namespace flite {
 
@@ -67,103 +66,16 @@ struct GemmParams {
     // lanes 0-63 = rows 0-63 x accumulator columns [0, N/2), lanes 64-127 = the same rows x columns [N/2, N), both at
     // TMEM columns [0, N/2).
     int narrow_m;
-    // EPI_GATED_RES: when ssq_out != nullptr the epilogue also writes, for every output row, the sum of squares of the
-    // bf16 values it stored, one fp32 slot per 64 output columns: ssq_out[row * ssq_ld + col / 64].  Every slot is
-    // written exactly once per launch (a thread covers two slots of a whole tile, one of a half-width / narrow unit), so
-    // the RMSNorm that follows (rmsnorm_modulate_ssq_kernel) sums N / 64 slots in a fixed order instead of re-reading the
-    // row: deterministic, batch-invariant, and the norm becomes a single pass over x.
-    float* ssq_out;
-    long long ssq_ld;
-    // EPI_GATED_RES + ssq_out: fused "RMSNorm + adaLN modulate of the finished rows" (nf_out != nullptr): the unit that
-    // stores the last missing columns of a CTA's rows of an M-block normalises them on the spot:
-    //   nf_out[row] = norm_w(x'[row]) * (1 + nf_scale[sample]) + nf_shift[sample]   (rmsnorm_modulate_ssq_kernel's math)
-    // nf_counters: [num M-blocks][2] uint32, zero between launches (reset by the unit that completes a count).
-    __nv_bfloat16* nf_out;
-    long long nf_ldo;
-    const __nv_bfloat16* nf_w;
-    int nf_wmode;                // 0 none, 1 Liger "llama" cast, 2 reference RMSNorm (fp32 weight multiply)
-    const __nv_bfloat16* nf_scale;
-    const __nv_bfloat16* nf_shift;
-    long long nf_ld_mod;
-    unsigned int* nf_counters;
-    int nf_debug;                // profiling experiments only: bit0 skip the norm job, bit1 skip the per-thread fence
     // L2 eviction-priority hints of the A / W tile loads (0 = plain load); chosen with the band height so that the operand
     // the rasterisation keeps resident is evict_last and the one that streams past it is evict_first.
     unsigned long long hint_a, hint_b;
 };
 
-__device__ unsigned long long g_nf_dbg[4];   // experiments: [0] max job ns, [1] sum job ns, [2] jobs, [3] units
-
-FLITE_DEVICE void norm_finished_rows(const GemmParams& p, int row0, int nrows, int warp, int lane) {
-    constexpr int MAXC = 12;                       // 16-byte chunks per lane and pass (d = 3072 in one pass)
-    const int d = p.N, nchunk = d >> 3, nslot = d >> 6;
-    const bool mod = p.nf_scale != nullptr;
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int rr = warp * 2; rr < nrows; rr += 16) {
-        int row[2];
-        bool ok[2];
-        float rstd[2];
-        const uint4* xr[2];
-        uint4* yr[2];
-        long long ms[2];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            row[t] = row0 + rr + t;
-            ok[t] = (rr + t < nrows) && row[t] < p.M;
-            const int r_ = ok[t] ? row[t] : row0;
-            xr[t] = reinterpret_cast<const uint4*>(p.C + (long long)r_ * p.ldc);
-            yr[t] = reinterpret_cast<uint4*>(p.nf_out + (long long)r_ * p.nf_ldo);
-            ms[t] = (long long)(r_ / p.rows_per_sample) * p.nf_ld_mod;
-            float part = 0.f;
-            if (ok[t])
-                for (int i = lane; i < nslot; i += 32) part += __ldcg(p.ssq_out + (long long)r_ * p.ssq_ld + i);
-            rstd[t] = part;
-        }
-        for (int c0 = 0; c0 < nchunk; c0 += MAXC * 32) {
-            uint4 v[2][MAXC];
-#pragma unroll
-            for (int t = 0; t < 2; ++t)
-#pragma unroll
-                for (int i = 0; i < MAXC; ++i) {
-                    const int c = c0 + lane + 32 * i;
-                    v[t][i] = (ok[t] && c < nchunk) ? __ldcg(xr[t] + c) : z;
-                }
-            if (c0 == 0) {
-#pragma unroll
-                for (int t = 0; t < 2; ++t) rstd[t] = rsqrtf(warp_sum(rstd[t]) / (float)d + p.eps);
-            }
-#pragma unroll
-            for (int i = 0; i < MAXC; ++i) {
-                const int c = c0 + lane + 32 * i;
-                if (c < nchunk) {
-                    const uint4 wv = p.nf_wmode != 0 ? __ldg(reinterpret_cast<const uint4*>(p.nf_w) + c) : z;
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        if (!ok[t]) continue;
-                        const uint4 scv = mod ? __ldg(reinterpret_cast<const uint4*>(p.nf_scale + ms[t]) + c) : z;
-                        const uint4 shv = mod ? __ldg(reinterpret_cast<const uint4*>(p.nf_shift + ms[t]) + c) : z;
-                        yr[t][c] = norm_mod_chunk(v[t][i], rstd[t], wv, p.nf_wmode, mod, scv, shv);
-                    }
-                }
-            }
-        }
-    }
-}
-
 constexpr int GEMM_BLOCK_K = 64;
-// warps: 0 TMA producer, 1 MMA issuer, 2..9 epilogue = TWO warpgroups that share every output row: in the QKV epilogue
-// (RoPE + QK-norm over a whole 256-column head per row) each owns one half of the (j, j+128) column pairs, in the others
-// each owns one contiguous half of the thread row's columns.
-__host__ __device__ constexpr int gemm_epi_warpgroups(int epi) { return 2; }
+// warps: 0 TMA producer, 1 MMA issuer, 2.. epilogue.  The QKV epilogue (RoPE + QK-norm over a whole 256-column head per
+// row) is the heaviest one: it runs on TWO warpgroups, each owning one half of the (j, j+128) column pairs of every row.
+__host__ __device__ constexpr int gemm_epi_warpgroups(int epi) { return epi == 3 ? 2 : 1; }
 __host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 128 * gemm_epi_warpgroups(epi); }
-
-// RMSNorm + modulate of `nrows` finished rows [row0, row0 + nrows) of the GEMM's output, run by the 8 epilogue warps of
-// the CTA whose unit completed them (GemmParams::nf_*).  Same arithmetic as rmsnorm_modulate_ssq_kernel: rstd from the
-// N / 64 sum-of-squares slots (lane i takes slots i, i + 32, ...; xor-shuffle tree), then norm_mod_chunk per 16 bytes.
-// Two rows per warp pass with all of their 16-byte loads in flight at once (the rows were written by other SMs a moment
-// ago: they come from L2, ld.global.cg).
-struct GemmParams;
-FLITE_DEVICE void norm_finished_rows(const GemmParams& p, int row0, int nrows, int warp, int lane);
 
 template <int kCtaGroup, int BLOCK_N, int kStages>
 struct GemmSmem {
@@ -367,22 +279,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int n_cols = narrow ? BLOCK_N / 2 : bn_eff;            // ... and how many (TMEM columns [0, n_cols))
             const int row = m0 + (narrow ? (q & 1) : q) * 32 + lane;
             const bool row_ok = row < p.M;
-            // Two epilogue warpgroups: warpgroup wg owns the contiguous half [wg * cpt, (wg + 1) * cpt) of this thread
-            // row's accumulator columns (cpt = 128 for a whole tile, 64 for a half-width / narrow unit), so the exposed
-            // epilogue of a cluster's last tile is half as long.
-            const int wg = (warp_idx - 2) >> 2;
-            const int cpt = n_cols >> 1;                 // accumulator columns per thread
-            const int tc0 = wg * cpt;                    // ... starting at this TMEM column of the thread's lanes
-            const int nc0 = n0 + tc0;                    // ... = this output column
-            (void)tc0; (void)nc0; (void)cpt;
-            // EPI_GATED_RES: the residual row slice does not depend on the accumulator: ALL of it (<= 16 x 16 bytes) is
-            // loaded before the wait for the accumulator, so its latency hides behind the mainloop; the per-sample gate
-            // and the bias (L1-resident after the first rows) are fetched one 32-column chunk ahead.
-            uint4 res_all[16], gate_n[4], bias_n[4];
+            // EPI_GATED_RES: the residual row slice, the per-sample gate and the bias do not depend on the accumulator;
+            // chunk c+1's loads are issued before chunk c is combined, and the first chunk's loads are issued before
+            // the wait for the accumulator itself, so their latency hides behind the mainloop / the previous chunk.
+            uint4 res_n[4], gate_n[4], bias_n[4];
             const __nv_bfloat16* gate_row = nullptr;
+            const __nv_bfloat16* res_row = nullptr;
             auto prefetch = [&](int col) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
+                    res_n[j] = row_ok ? __ldcg(reinterpret_cast<const uint4*>(res_row + col) + j) : make_uint4(0, 0, 0, 0);
                     gate_n[j] = __ldg(reinterpret_cast<const uint4*>(gate_row + col) + j);
                     bias_n[j] = p.bias != nullptr ? __ldg(reinterpret_cast<const uint4*>(p.bias + col) + j)
                                                   : make_uint4(0, 0, 0, 0);
@@ -390,34 +296,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             };
             if constexpr (kEpi == EPI_GATED_RES) {
                 gate_row = p.gate + (long long)((row_ok ? row : 0) / p.rows_per_sample) * p.ld_gate;
-                const uint4* res_row = reinterpret_cast<const uint4*>(p.resid + (long long)(row_ok ? row : 0) * p.ldr + nc0);
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    res_all[j] = (row_ok && j * 8 < cpt) ? __ldcg(res_row + j) : make_uint4(0, 0, 0, 0);
-                prefetch(nc0);
+                res_row = p.resid + (long long)(row_ok ? row : 0) * p.ldr;
+                prefetch(n0);
             }
             mbar_wait<kCtaGroup == 2>(&tmem_full_bar[acc], acc_phase, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
 
             if constexpr (kEpi == EPI_GATED_RES) {
-                // x' = x + bf16(bf16(acc + bias) * gate)
-                float ss = 0.f;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c * 32 >= cpt) break;
+                // x' = x + bf16(bf16(acc + bias) * gate); operands prefetched above / one chunk ahead
+#pragma unroll 1
+                for (int c = 0; c < n_cols / 32; ++c) {
                     uint32_t r[32];
-                    tmem_ld_x32(taddr + tc0 + c * 32, r);
+                    tmem_ld_x32(taddr + c * 32, r);
                     uint32_t res_p[16], gate_p[16], bias_p[16];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint4 rv = res_all[4 * c + j];
-                        res_p[4 * j] = rv.x; res_p[4 * j + 1] = rv.y; res_p[4 * j + 2] = rv.z; res_p[4 * j + 3] = rv.w;
+                        res_p[4 * j] = res_n[j].x; res_p[4 * j + 1] = res_n[j].y; res_p[4 * j + 2] = res_n[j].z; res_p[4 * j + 3] = res_n[j].w;
                         gate_p[4 * j] = gate_n[j].x; gate_p[4 * j + 1] = gate_n[j].y; gate_p[4 * j + 2] = gate_n[j].z; gate_p[4 * j + 3] = gate_n[j].w;
                         bias_p[4 * j] = bias_n[j].x; bias_p[4 * j + 1] = bias_n[j].y; bias_p[4 * j + 2] = bias_n[j].z; bias_p[4 * j + 3] = bias_n[j].w;
                     }
-                    const int col = nc0 + c * 32;
-                    if ((c + 1) * 32 < cpt) prefetch(col + 32);
+                    const int col = n0 + c * 32;
+                    if (c + 1 < n_cols / 32) prefetch(col + 32);
                     tmem_ld_wait();
                     uint32_t outp[16];
 #pragma unroll
@@ -428,9 +328,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         a = bf16_round(a * bf16_lo(gate_p[j]));
                         b = bf16_round(b * bf16_hi(gate_p[j]));
                         outp[j] = pack_bf16x2(bf16_lo(res_p[j]) + a, bf16_hi(res_p[j]) + b);
-                        const float v0 = bf16_lo(outp[j]), v1 = bf16_hi(outp[j]);     // the values as stored
-                        ss = fmaf(v0, v0, ss);
-                        ss = fmaf(v1, v1, ss);
                     }
                     if (row_ok) {
                         uint4* cp = reinterpret_cast<uint4*>(p.C + (long long)row * p.ldc + col);
@@ -438,64 +335,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int j = 0; j < 4; ++j)
                             cp[j] = make_uint4(outp[4 * j], outp[4 * j + 1], outp[4 * j + 2], outp[4 * j + 3]);
                     }
-                    if (c & 1) {                 // a 64-column slot is complete
-                        if (p.ssq_out != nullptr && row_ok) p.ssq_out[(long long)row * p.ssq_ld + (col >> 6)] = ss;
-                        ss = 0.f;
-                    }
                 }
-                // hand the accumulator back to the MMA warp before anything else
-                tc_fence_before();
-                __syncwarp();
-                if (elect_one()) {
-                    if constexpr (kCtaGroup == 1) mbar_arrive(&tmem_empty_bar[acc]);
-                    else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
-                }
-                __syncwarp();
-                if (p.nf_out != nullptr) {
-                    // Fused RMSNorm + modulate of FINISHED rows: every unit that covers this CTA's rows of M-block m_blk
-                    // adds its width (2 per whole tile, 1 per half-width unit) to a counter; the unit that completes
-                    // the count (all N / BLOCK_N tiles stored, rows and ssq slots visible through the fence / atomic
-                    // chain) normalises those rows right away -- while they are still in L2 and while the MMA warp
-                    // runs the next tile -- and resets the counter for the next launch.
-                    unsigned int* flag = reinterpret_cast<unsigned int*>(smem + S::BAR_OFFSET + 192);
-                    if (!(p.nf_debug & 2)) __threadfence();
-                    named_bar_sync(5, 256);
-                    if (threadIdx.x == 64) {
-                        unsigned int* cnt = p.nf_counters + (m_blk * 2 + (int)cta_rank);
-                        const unsigned int inc = (half < 0) ? 2u : 1u, total = 2u * (unsigned)num_n_tiles;
-                        const unsigned int old = atomicAdd(cnt, inc);
-                        const bool last = old + inc == total;
-                        if (last) {
-                            *cnt = 0u;
-                            __threadfence();
-                        }
-                        *flag = last ? 1u : 0u;
-                    }
-                    named_bar_sync(5, 256);
-                    if ((p.nf_debug & 4) && threadIdx.x == 64) atomicAdd(&g_nf_dbg[3], 1ull);
-                    if (*flag != 0u && !(p.nf_debug & 1)) {
-                        const int rows_here = narrow ? 64 : 128;
-                        const uint64_t t0 = (p.nf_debug & 4) ? globaltimer_ns() : 0;
-                        norm_finished_rows(p, m0, rows_here, (warp_idx - 2), lane);
-                        if (p.nf_debug & 4) {
-                            named_bar_sync(5, 256);
-                            if (threadIdx.x == 64) {
-                                const unsigned long long dt = globaltimer_ns() - t0;
-                                atomicMax(&g_nf_dbg[0], dt);
-                                atomicAdd(&g_nf_dbg[1], dt);
-                                atomicAdd(&g_nf_dbg[2], 1ull);
-                            }
-                        }
-                    }
-                }
-                continue;   // barrier already signalled
             } else if constexpr (kEpi == EPI_STORE) {
 #pragma unroll 1
-                for (int c = 0; c < cpt / 32; ++c) {
+                for (int c = 0; c < n_cols / 32; ++c) {
                     uint32_t r[32];
-                    tmem_ld_x32(taddr + tc0 + c * 32, r);
+                    tmem_ld_x32(taddr + c * 32, r);
                     tmem_ld_wait();
-                    const int col = nc0 + c * 32;
+                    const int col = n0 + c * 32;
                     uint32_t outp[16];
                     uint32_t bias_p[16];
                     if (p.bias != nullptr) {
@@ -524,12 +371,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
             } else if constexpr (kEpi == EPI_SWIGLU) {
-                // weight rows are interleaved in groups of 64: [gate 64 | up 64] per 128 accumulator columns; the
-                // (group, 32-pair half) items of this thread row are split between the two warpgroups
+                // weight rows are interleaved in groups of 64: [gate 64 | up 64] per 128 accumulator columns
                 static_assert(kEpi != EPI_SWIGLU || BLOCK_N % 128 == 0, "SwiGLU epilogue needs 128-column groups");
-                const int items = n_cols / 64, per_wg = items >> 1;
 #pragma unroll 1
-                for (int c = wg * per_wg; c < (wg + 1) * per_wg; ++c) {
+                for (int c = 0; c < n_cols / 64; ++c) {
                     const int grp = c >> 1, hf = c & 1;
                     uint32_t g[32], u[32];
                     tmem_ld_x32(taddr + grp * 128 + hf * 32, g);

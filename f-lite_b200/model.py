@@ -191,10 +191,6 @@ class DiT(nn.Module):
         # "auto" (FLITE_ATTN_STREAMK=auto) turns it on when the per-tile grid wastes >= 10 % of its last wave on long
         # sequences; "1" forces it.
         self.attn_streamk = os.environ.get("FLITE_ATTN_STREAMK", "0")
-        # gated-residual GEMM epilogues emit per-row sum-of-squares slots, the RMSNorm after them is single-pass
-        self.fused_norm_stats = os.environ.get("FLITE_FUSED_NORM_STATS", "1") != "0"
-        # ... and the GEMM unit that completes a block of rows normalises + modulates them for the next GEMM itself
-        self.fused_norm = os.environ.get("FLITE_FUSED_NORM", "1") != "0"
         self.gemm_variant = GEMM_AUTO
         self.sp_group = None      # Ulysses sequence-parallel process group (see enable_sequence_parallel)
         self.sp_fused = False     # exchanges fused into the kernels over NVLink peer memory instead of NCCL
@@ -242,14 +238,6 @@ class DiT(nn.Module):
             ao = sym.local[recv_elems:recv_elems + B * Lq * d].view(B * Lq, d)
             self._sp_sym = (key, sym, recv, ao, sym.table(0), sym.table(2 * recv_elems))
         return self._sp_sym[1:]
-
-    def _ssq_buf(self, T, d, device):
-        key = ("ssq", T, d // 64)
-        b = self._ws.get(key)
-        if b is None or b.device != device:
-            b = torch.empty((T, d // 64), dtype=torch.float32, device=device)      # one slot per 64 columns
-            self._ws[key] = b
-        return b
 
     def _use_streamk(self, B, heads, L):
         mode = self.attn_streamk
@@ -475,30 +463,9 @@ class DiT(nn.Module):
         fmod = ops.gemm(st, fm.weight, fm.bias, variant=v)                   # [B, 2d]
         (shift_sa, scale_sa, gate_sa, shift_ca, scale_ca, gate_ca, shift_mlp, scale_mlp, gate_mlp) = (
             mod[:, k * d:(k + 1) * d] for k in range(9))
-        fshift, fscale = fmod[:, :d], fmod[:, d:]
 
         nbuf = self._buf("n", (T, d), dev)
         abuf = self._buf("attn", (T, d), dev)
-        # per-row sum-of-squares slots of the residual stream (one per 64 columns), written by every gated-residual GEMM
-        # epilogue and consumed by the single-pass RMSNorm that follows it (FLITE_FUSED_NORM_STATS=0: two-pass norm)
-        ssq = self._ssq_buf(T, d, dev) if (self.fused_norm_stats and d % 128 == 0) else None
-        ssq_ok = False          # the slots describe the current xs (false until the first gated-residual GEMM has run)
-        # ... and the GEMM unit that completes a block of rows also normalises + modulates them for the NEXT consumer
-        # (straight into nbuf, rows still in L2), so the 2 - 3 norm launches per block disappear (FLITE_FUSED_NORM=0: off)
-        fuse_norm = ssq is not None and self.fused_norm
-        if fuse_norm:
-            cnt = self._ws.get(("nf_counters", T))
-            if cnt is None or cnt.device != dev:
-                cnt = torch.zeros(2 * ((T + 127) // 128), dtype=torch.int32, device=dev)
-                self._ws[("nf_counters", T)] = cnt
-
-        def next_norm(weight, mode, sc, sh):
-            if not fuse_norm:
-                return None
-            return dict(out=nbuf, weight=weight, weight_mode=mode, scale=sc, shift=sh, counters=cnt)
-
-        n_ready = False         # nbuf already holds the normalised + modulated input of the next GEMM
-        fw = self.final_norm.weight
         qc = self._buf("qc", (T, d), dev)
         inter = self.blocks[0].mlp.gate_proj.weight.shape[0] if len(self.blocks) else 0
         hmid = self._buf("hmid", (T, inter), dev)
@@ -530,13 +497,8 @@ class DiT(nn.Module):
         x_variant = ATTN_XRES if (ctx.Lc <= 256 and ops.get_tuning(12) == ATTN_XRES) else 0
         for i, blk in enumerate(self.blocks):
             # ---- self-attention (model.py:283-289)
-            if not n_ready:
-                ops.rmsnorm_modulate(xs, blk.norm1.weight, 1, scale_sa, shift_sa, rows_per_sample=Lq, out=nbuf,
-                                     ssq=ssq if ssq_ok else None)
+            ops.rmsnorm_modulate(xs, blk.norm1.weight, 1, scale_sa, shift_sa, rows_per_sample=Lq, out=nbuf)
             sa = blk.self_attn
-            # what follows the self-attention residual: norm2 (cross-attention blocks) or norm3
-            nn_sa = (next_norm(blk.norm2.weight, 1, scale_ca, shift_ca) if blk.cross_attn is not None
-                     else next_norm(blk.norm3.weight, 1, scale_mlp, shift_mlp))
             if sp is None:
                 ops.gemm(nbuf, sa.qkv.weight, sa.qkv.bias, epilogue=EPI_QKV_ROPE, rope_cos=cos, rope_sin=sin,
                          qk_cols=2 * d, rows_per_sample=Lq, variant=v, out=qkv)
@@ -557,7 +519,7 @@ class DiT(nn.Module):
                                              cu_full, hq, L, scale, ao_tab, P, Lq, rk * hq, d)
                 sym.exchange_done(stream)
                 ops.gemm(p2p_ao, sa.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_sa,
-                         rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq, norm=nn_sa)
+                         rows_per_sample=Lq, variant=v, out=xs)
             else:
                 # Ulysses: the QKV epilogue scatters heads into the all-to-all send layout; after the exchange this
                 # rank holds q|k|v of its hq heads for the FULL sequence; the second exchange returns the outputs.
@@ -579,41 +541,27 @@ class DiT(nn.Module):
                     ops.permute_021(ao_recv[b].view(P, Lq, dq), out=abuf[b * Lq:(b + 1) * Lq].view(Lq, P, dq))
             if not (sp is not None and self.sp_fused):
                 ops.gemm(abuf, sa.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_sa,
-                         rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq, norm=nn_sa)
-            ssq_ok = ssq is not None
-            n_ready = nn_sa is not None
+                         rows_per_sample=Lq, variant=v, out=xs)
             # ---- cross-attention (model.py:291-297): token-local, context K/V replicated
             if blk.cross_attn is not None:
                 ca = blk.cross_attn
-                if not n_ready:
-                    ops.rmsnorm_modulate(xs, blk.norm2.weight, 1, scale_ca, shift_ca, rows_per_sample=Lq, out=nbuf,
-                                         ssq=ssq if ssq_ok else None)
+                ops.rmsnorm_modulate(xs, blk.norm2.weight, 1, scale_ca, shift_ca, rows_per_sample=Lq, out=nbuf)
                 ops.gemm(nbuf, ca.q.weight, ca.q.bias, epilogue=EPI_QKV_ROPE, qk_cols=d, rows_per_sample=Lq,
                          variant=v, out=qc)
                 ck, cv = ctx.kvs[i]
                 ops.attention_varlen(qc, ck, cv, cu_x, ctx.cu_k, nh, Lq, scale, out=abuf, variant=x_variant)
-                nn_ca = next_norm(blk.norm3.weight, 1, scale_mlp, shift_mlp)
                 ops.gemm(abuf, ca.proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_ca,
-                         rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq, norm=nn_ca)
-                n_ready = nn_ca is not None
+                         rows_per_sample=Lq, variant=v, out=xs)
             # ---- SwiGLU MLP (model.py:299-301)
-            if not n_ready:
-                ops.rmsnorm_modulate(xs, blk.norm3.weight, 1, scale_mlp, shift_mlp, rows_per_sample=Lq, out=nbuf,
-                                     ssq=ssq if ssq_ok else None)
+            ops.rmsnorm_modulate(xs, blk.norm3.weight, 1, scale_mlp, shift_mlp, rows_per_sample=Lq, out=nbuf)
             ops.gemm(nbuf, self._gate_up(i, blk), None, epilogue=EPI_SWIGLU, variant=v, out=hmid)
-            # what follows the MLP residual: the next block's norm1, or the final norm + final modulation
-            if i + 1 < len(self.blocks):
-                nn_mlp = next_norm(self.blocks[i + 1].norm1.weight, 1, scale_sa, shift_sa)
-            else:
-                nn_mlp = next_norm(fw, 2 if fw is not None else 0, fscale, fshift)
             ops.gemm(hmid, blk.mlp.down_proj.weight, None, epilogue=EPI_GATED_RES, resid=xs, gate=gate_mlp,
-                     rows_per_sample=Lq, variant=v, out=xs, ssq_out=ssq, norm=nn_mlp)
-            n_ready = nn_mlp is not None
+                     rows_per_sample=Lq, variant=v, out=xs)
 
         # ---- final head (model.py:577-590)
-        if not n_ready:
-            ops.rmsnorm_modulate(xs, fw, 2 if fw is not None else 0, fscale, fshift, rows_per_sample=Lq, out=nbuf,
-                                 ssq=ssq if ssq_ok else None)
+        fshift, fscale = fmod[:, :d], fmod[:, d:]
+        fw = self.final_norm.weight
+        ops.rmsnorm_modulate(xs, fw, 2 if fw is not None else 0, fscale, fshift, rows_per_sample=Lq, out=nbuf)
         o = ops.gemm(nbuf, self.final_proj.weight, self.final_proj.bias, variant=v)
         if sp is not None:
             # gather every rank's token slice: [rank][sample][Lq*64] -> [sample][rank][Lq*64] = [B*L, 64]

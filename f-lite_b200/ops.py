@@ -168,11 +168,8 @@ def image_to_uint8(decoded: torch.Tensor, out: Optional[torch.Tensor] = None) ->
 @_traced(lambda x, *a, **k: f"rmsnorm_modulate {tuple(x.shape)}")
 def rmsnorm_modulate(x: torch.Tensor, weight: Optional[torch.Tensor], weight_mode: int,
                      scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
-                     rows_per_sample: int = 0, eps: float = 1e-6, out: Optional[torch.Tensor] = None,
-                     ssq: Optional[torch.Tensor] = None):
-    """x [rows, d]; scale/shift are [B, d] views into the modulation matrix (same row stride).
-    ``ssq`` [rows, >= d/64] fp32: per-row sum-of-squares slots written by the gated-residual GEMM that produced ``x``
-    (``gemm(..., ssq_out=)``): the single-pass kernel, which does not reduce the row itself."""
+                     rows_per_sample: int = 0, eps: float = 1e-6, out: Optional[torch.Tensor] = None):
+    """x [rows, d]; scale/shift are [B, d] views into the modulation matrix (same row stride)."""
     lib = _lib.load()
     _chk(x, "x")
     rows, d = x.shape
@@ -185,13 +182,6 @@ def rmsnorm_modulate(x: torch.Tensor, weight: Optional[torch.Tensor], weight_mod
         ld_mod = scale.stride(0)
         if shift.stride(0) != ld_mod:
             raise _lib.FliteError("scale and shift must share a row stride")
-    if ssq is not None:
-        _chk(ssq, "ssq", torch.float32)
-        _lib.check(lib.flite_rmsnorm_modulate_ssq(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), _ptr(weight),
-                                                  weight_mode, _ptr(scale), _ptr(shift), ld_mod, rows_per_sample, rows, d,
-                                                  eps, ssq.data_ptr(), ssq.stride(0), _stream()), "rmsnorm_modulate_ssq")
-        LAUNCHES[0] += 1
-        return out
     _lib.check(lib.flite_rmsnorm_modulate(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), _ptr(weight),
                                           weight_mode, _ptr(scale), _ptr(shift), ld_mod, rows_per_sample, rows, d,
                                           eps, _stream()), "rmsnorm_modulate")
@@ -313,14 +303,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          epilogue: int = EPI_STORE, resid: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
          rows_per_sample: int = 0, rope_cos: Optional[torch.Tensor] = None, rope_sin: Optional[torch.Tensor] = None,
          qk_cols: int = 0, eps: float = 1e-6, variant: int = GEMM_AUTO, out: Optional[torch.Tensor] = None,
-         sp_ranks: int = 0, sp_heads_per_rank: int = 0, ssq_out: Optional[torch.Tensor] = None,
-         norm: Optional[dict] = None):
-    """out = epilogue(a @ w.T); a [M, K], w [N, K] (nn.Linear layout), bf16.
-    ``ssq_out`` [M, >= N/64] fp32 (EPI_GATED_RES only): also emit the per-row sum of squares of the stored rows, one slot
-    per 64 columns, for the single-pass ``rmsnorm_modulate(..., ssq=)`` that follows.
-    ``norm`` (with ``ssq_out``): ``dict(out=, weight=, weight_mode=, scale=, shift=, counters=)`` -- the GEMM unit that
-    completes a block of rows also writes ``norm_w(x') * (1 + scale) + shift`` for them into ``out`` (the RMSNorm + adaLN
-    modulate that follows the residual update in the reference, model.py:283-301), so no norm launch is needed."""
+         sp_ranks: int = 0, sp_heads_per_rank: int = 0):
+    """out = epilogue(a @ w.T); a [M, K], w [N, K] (nn.Linear layout), bf16."""
     lib = _lib.load()
     _chk(a, "a")
     _chk(w, "w")
@@ -343,32 +327,6 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     hook = PROFILE_HOOK
     if hook is not None:
         hook("gemm", "begin", (M, N, K, epilogue))
-    if ssq_out is not None:
-        if epilogue != EPI_GATED_RES:
-            raise _lib.FliteError("gemm: ssq_out goes with the gated-residual epilogue")
-        _chk(ssq_out, "ssq_out", torch.float32)
-        if norm is not None:
-            n_out, n_w, n_sc, n_sh = norm["out"], norm.get("weight"), norm.get("scale"), norm.get("shift")
-            _chk(n_out, "norm.out")
-            _chk(norm["counters"], "norm.counters", torch.int32)
-            _lib.check(lib.flite_gemm_gated_res_norm(
-                a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), M, N, K, _ptr(bias),
-                resid.data_ptr(), resid.stride(0), gate.data_ptr(), gate.stride(0), rows_per_sample, ssq_out.data_ptr(),
-                ssq_out.stride(0), n_out.data_ptr(), n_out.stride(0), _ptr(n_w), int(norm.get("weight_mode", 1)), _ptr(n_sc),
-                _ptr(n_sh), n_sc.stride(0) if n_sc is not None else 0, float(eps), norm["counters"].data_ptr(), variant,
-                _stream()), "gemm_gated_res_norm")
-            LAUNCHES[0] += 1
-            if hook is not None:
-                hook("gemm", "end", (M, N, K, epilogue))
-            return out
-        _lib.check(lib.flite_gemm_gated_res_ssq(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
-                                                out.stride(0), M, N, K, _ptr(bias), resid.data_ptr(), resid.stride(0),
-                                                gate.data_ptr(), gate.stride(0), rows_per_sample, ssq_out.data_ptr(),
-                                                ssq_out.stride(0), variant, _stream()), "gemm_gated_res_ssq")
-        LAUNCHES[0] += 1
-        if hook is not None:
-            hook("gemm", "end", (M, N, K, epilogue))
-        return out
     _lib.check(lib.flite_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
                                    out.stride(0), M, N, K, _ptr(bias), act, epilogue, _ptr(resid),
                                    resid.stride(0) if resid is not None else 0, _ptr(gate),

@@ -172,27 +172,6 @@ int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
                     const void* rope_sin, int qk_cols, float eps, int sp_ranks, int sp_heads_per_rank, int variant,
                     void* stream);
 
-/* Gated-residual GEMM (EPI_GATED_RES of flite_gemm_bf16: x' = resid + bf16(bf16(A W^T + bias) * gate)) that ALSO emits the
- * per-row sum of squares of the x' it stored, one fp32 slot per 64 output columns (ssq_out[row * ssq_ld + col / 64],
- * N % 128 == 0, every slot written once), and the single-pass RMSNorm + adaLN modulate that consumes those slots
- * instead of reducing the row itself (same rounding points as flite_rmsnorm_modulate; the slot sum has a fixed order).
- * flite_gemm_gated_res_norm goes one step further: the unit of the GEMM that stores the last missing columns of a block
- * of rows normalises + modulates those rows itself, while they are still in L2 (norm_out must not alias C; `counters`:
- * 2 * ceil(M / 128) uint32, zero-filled once by the caller, left zeroed by every launch).  Bit-identical to the
- * two-launch form.  Together they replace
- *     x = x + f(n) * gate ; n = LigerRMSNorm(x) * (1 + scale) + shift                          model.py:283-301 */
-int flite_gemm_gated_res_ssq(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N,
-                             int K, const void* bias, const void* resid, int64_t ldr, const void* gate, int64_t ld_gate,
-                             int rows_per_sample, float* ssq_out, int64_t ssq_ld, int variant, void* stream);
-int flite_gemm_gated_res_norm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N,
-                              int K, const void* bias, const void* resid, int64_t ldr, const void* gate, int64_t ld_gate,
-                              int rows_per_sample, float* ssq_out, int64_t ssq_ld, void* norm_out, int64_t ld_norm_out,
-                              const void* norm_w, int weight_mode, const void* scale, const void* shift, int64_t ld_mod,
-                              float eps, unsigned int* counters, int variant, void* stream);
-int flite_rmsnorm_modulate_ssq(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w, int weight_mode,
-                               const void* scale, const void* shift, int64_t ld_mod, int rows_per_sample, int rows,
-                               int d, float eps, const float* ssq, int64_t ld_ssq, void* stream);
-
 /* Varlen non-causal flash attention, head_dim 256.                                        model.py:203-211
  *   q[rows_q, ldq] head h at columns q_col0 + 256 h (same for k, v); cu_q / cu_k int32 [B+1] on device;
  *   out[rows_q, ldo] head-major columns; max_q = longest query sequence (host value). */

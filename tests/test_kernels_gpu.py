@@ -692,50 +692,3 @@ def test_attention_streamk_rejects_ragged_lengths():
     ops.attention_streamk(q, k, v, cu, cu, H, 300, 300, 256 ** -0.5)
     with pytest.raises(_lib.FliteError):
         _lib.watchdog_ok()
-
-
-@pytest.mark.parametrize("M,d,K", [(8224, 3072, 3072), (300, 512, 1024), (4100, 1024, 512), (96, 512, 512)])
-def test_gated_residual_gemm_emits_ssq_slots_for_single_pass_rmsnorm(M, d, K):
-    """flite_gemm_gated_res_ssq + flite_rmsnorm_modulate_ssq: the epilogue's per-row, per-64-column sum-of-squares slots
-    equal the sums recomputed from the rows it stored, the GEMM output is bit-identical to the plain gated-residual GEMM,
-    and the single-pass norm agrees with the two-pass kernel (same rounding points; only the fp32 summation order of
-    sum(x^2) differs => rare 1-ulp flips)."""
-    from flite_b200 import ops
-    B = 2
-    g = torch.Generator(device=DEV).manual_seed(M + d)
-    a = (torch.randn(M, K, device=DEV, generator=g) * 0.5).bfloat16()
-    w = (torch.randn(d, K, device=DEV, generator=g) * 0.05).bfloat16()
-    gate = torch.randn(B, d, device=DEV, generator=g).bfloat16()
-    x0 = torch.randn(M, d, device=DEV, generator=g).bfloat16()
-    rps = (M + B - 1) // B
-    plain = x0.clone()
-    ops.gemm(a, w, None, epilogue=ops.EPI_GATED_RES, resid=plain, gate=gate, rows_per_sample=rps, out=plain)
-    x = x0.clone()
-    ssq = torch.full((M, d // 64), -1.0, dtype=torch.float32, device=DEV)
-    ops.gemm(a, w, None, epilogue=ops.EPI_GATED_RES, resid=x, gate=gate, rows_per_sample=rps, out=x, ssq_out=ssq)
-    assert torch.equal(x, plain)
-    ref = x.float().pow(2).view(M, d // 64, 64).sum(-1)
-    assert bool((ssq >= 0).all())
-    assert ((ssq - ref).abs() / ref.clamp_min(1e-6)).max().item() <= 1e-5
-    nw = (1 + 0.1 * torch.randn(d, device=DEV, generator=g)).bfloat16()
-    mod = (0.2 * torch.randn(B, 2 * d, device=DEV, generator=g)).bfloat16()
-    two = ops.rmsnorm_modulate(x, nw, 1, mod[:, :d], mod[:, d:], rows_per_sample=rps)
-    one = ops.rmsnorm_modulate(x, nw, 1, mod[:, :d], mod[:, d:], rows_per_sample=rps, ssq=ssq)
-    assert (one == two).float().mean().item() > 0.999 and rel(one, two) <= 2e-4
-    one2 = ops.rmsnorm_modulate(x, nw, 2, ssq=ssq)
-    assert rel(one2, ops.rmsnorm_modulate(x, nw, 2)) <= 2e-4
-    # flite_gemm_gated_res_norm: the GEMM unit that completes a block of rows normalises them itself -- same bits as the
-    # GEMM followed by the single-pass norm, twice in a row (the completion counters reset themselves)
-    cnt = torch.zeros(2 * ((M + 127) // 128), dtype=torch.int32, device=DEV)
-    for wmode, sc, sh in ((1, mod[:, :d], mod[:, d:]), (2, None, None), (0, mod[:, :d], mod[:, d:])):
-        want = ops.rmsnorm_modulate(x, nw if wmode else None, wmode, sc, sh, rows_per_sample=rps, ssq=ssq)
-        for _ in range(2):
-            x2 = x0.clone()
-            ssq2 = torch.full_like(ssq, -1.0)
-            fused = torch.full((M + 4, d), 7.0, dtype=torch.bfloat16, device=DEV)
-            ops.gemm(a, w, None, epilogue=ops.EPI_GATED_RES, resid=x2, gate=gate, rows_per_sample=rps, out=x2, ssq_out=ssq2,
-                     norm=dict(out=fused[:M], weight=nw if wmode else None, weight_mode=wmode, scale=sc, shift=sh,
-                               counters=cnt))
-            assert torch.equal(x2, plain) and torch.equal(ssq2, ssq)
-            assert torch.equal(fused[:M], want), f"fused norm differs (weight_mode {wmode})"
-            assert bool((fused[M:] == 7.0).all()) and int(cnt.abs().sum().item()) == 0

@@ -540,25 +540,3 @@ def test_batch4_per_gpu_layout_is_bit_identical_to_per_image_runs():
     finally:
         m.attn_streamk = "0"
     assert rel(v1, v0) <= TOL
-
-
-def test_fused_norm_paths_are_bit_identical():
-    """The three forms of "residual update -> RMSNorm -> modulate" (model.py:283-301) give the same bits: norm launches
-    that reduce the row themselves apart (their sum order differs: <= tolerance), the single-pass norm on the epilogue's
-    sum-of-squares slots and the norm fused into the GEMM unit that completes the rows are bit-identical."""
-    from oracle import synth
-    cfg = dict(synth.ARCH_10B, depth=3)
-    sd = synth.make_state_dict(cfg, 0, device=DEV)
-    m = _model(cfg, sd)
-    x, ctx, mask = synth.make_inputs(cfg, 1, 512, 768, 64, valid_len=[50], device=DEV)
-    xb, cb, mb = torch.cat([x, x]).bfloat16(), ctx.bfloat16(), mask.bfloat16()
-    t = torch.full((2,), 0.4, device=DEV).bfloat16()
-    fused = m(xb, cb, mb, t)
-    m.fused_norm = False
-    slots = m(xb, cb, mb, t)
-    m.fused_norm_stats = False
-    two_pass = m(xb, cb, mb, t)
-    m.fused_norm = m.fused_norm_stats = True
-    assert torch.equal(fused, slots)
-    assert rel(two_pass, fused) <= TOL
-    assert torch.equal(m(xb, cb, mb, t), fused)
