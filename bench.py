@@ -552,13 +552,14 @@ def multi_gpu_layouts(model, dev, world, rank, steps):
         sk = None
         if sp_group is not None and model._use_streamk_auto(1 if cfg_group is not None else 2,
                                                             arch["num_heads"] // sp_ranks, 16 + (height // 16) * (width // 16)):
+            sk_default = model.attn_streamk
             model.attn_streamk = "auto"
             lat, acc = lat0.clone(), lat0.clone()
             v_sk = flite_b200.denoise_step(model, lat, acc, ctx_in, mask_in, t_in, 0.01, GUIDANCE, True, cfg_group=cfg_group).clone()
             r_sk = torch.tensor([rel(v_sk, v1)], device=dev, dtype=torch.float64)
             dist.all_reduce(r_sk, op=dist.ReduceOp.MAX)
             ms_sk = timed(step, n)
-            model.attn_streamk = "0"
+            model.attn_streamk = sk_default
             sk = {"ms_per_step": ms_sk, "speedup_vs_1gpu": ms1 / ms_sk, "rel_l2_vs_1gpu": float(r_sk.item())}
         _lib.watchdog_ok()
         model.enable_sequence_parallel(None)

@@ -22,7 +22,8 @@ constexpr int ATT2_SQ = 0, ATT2_SK = 65536, ATT2_SV = 131072, ATT2_SP = 196608;
 template <int kWG, bool kPTmem>
 __global__ void __launch_bounds__(64 + 128 * kWG, 1)
 attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                    const AttnParams p) {
     const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
     pdl_launch_dependents();   // PDL: the next kernel may be scheduled as SMs drain; it waits for this grid to finish
     pdl_wait();                // q/k/v (and cu_seqlens) come from earlier kernels of the stream
@@ -304,7 +305,37 @@ attn_fwd_cg2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             mbar_wait<true>(pv_done, (n_tiles - 1) & 1, 29);
             tc_fence_after();
             const float inv_l = 1.0f / l;
-            if (p.stage_out) {
+            if (p.tma_out && qt * 128 + 128 <= q_len) {
+                // Whole tile (uniform for the CTA): O / l -> bf16 -> the Q region (dead: every MMA has retired), laid out as
+                // four [128 rows x 64 columns] boxes with the 128-byte swizzle of the tensor map; one thread issues the
+                // four TMA stores.  Conflict-free st.shared (16-byte chunk index XOR row), no per-thread global stores.
+#pragma unroll 1
+                for (int c = 0; c < OC / 32; ++c) {
+                    uint32_t o[32];
+                    tmem_ld_x32(tmem_o + lane_off + half * OC + c * 32, o);
+                    tmem_ld_wait();
+                    const int col = half * OC + c * 32;                      // first of 32 output columns
+                    uint8_t* box = smem + ATT2_SQ + (col >> 6) * 16384 + r * 128;
+                    const int ch0 = (col & 63) >> 3;                         // first 16-byte chunk inside the 128-byte row
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(box + (((ch0 + i) ^ (r & 7)) << 4)) = make_uint4(
+                            pack_bf16x2(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(5, 128 * kWG);
+                if (warp_idx == 2 && elect_one()) {
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb)
+                        tma_store_2d(&tmap_o, smem + ATT2_SQ + cb * 16384, h * 256 + cb * 64, q_beg + qt * 128);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();      // shared memory must stay valid until the bulk stores have read it
+                }
+                __syncwarp();
+            } else if (p.stage_out) {
                 // Whole-row stores (NVLink peer destinations): all MMAs have completed (pv_done), so the Q tile in
                 // shared memory is dead; each warp transposes its 32 rows through it -- lane = row on the way in,
                 // lane = 16-byte chunk on the way out (32 / CH rows of OC*2 contiguous bytes per store instruction).

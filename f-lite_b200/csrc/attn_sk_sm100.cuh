@@ -38,6 +38,13 @@ struct AttnSkParams {
     int q_len, k_len;      // uniform per-sequence lengths
     int QT, NT;            // 256-row query tiles / 128-key tiles per (sequence, head)
     long long total;       // B * H * QT * NT tile-steps
+    // Schedule: units [0, rr_units) are run WHOLE, round-robin (cluster c takes units c, c + C, c + 2C, ...: neighbouring
+    // clusters walk the same key tiles of neighbouring query tiles in lock step, exactly like the one-cluster-per-unit
+    // launch, and no unit of this part is split); the tile-steps of the remaining units are cut into equal contiguous
+    // shares (stream-K).  rr_units = 0: pure stream-K; rr_units = all units: persistent, never splits a unit.
+    long long rr_units;
+    int debug;             // profiling experiments only (0 in production): bit3 = skip the epilogue of whole units
+    int tma_out;           // 1 = whole units with 128 valid rows per CTA leave through shared memory + TMA box stores
     unsigned int* flags;   // workspace head: [cluster slot][cta rank], zero when idle
     float* slots;          // workspace body: [cluster slot][SK_SLOT_FLOATS]
     // Fused Ulysses return path (as in attn_fwd_cg2_kernel): when out_peer[0] != nullptr query row l of this rank's heads
@@ -48,9 +55,34 @@ struct AttnSkParams {
     int sp_head0;
 };
 
-__global__ void __launch_bounds__(192, 1)
+// The segment walk of one cluster, identical in every warp role: whole units of the round-robin part first, then the
+// cluster's contiguous share [t, t_end) of the remaining tile-steps.  A segment is (unit u, key tiles [j0, j1)).
+struct SkWalk {
+    long long u_rr, rr_units, t, t_end;
+    int C, NT;
+    FLITE_DEVICE SkWalk(const AttnSkParams& p, int cluster_id, int num_clusters) {
+        C = num_clusters; NT = p.NT;
+        u_rr = cluster_id; rr_units = p.rr_units;
+        const long long t_off = p.rr_units * NT, rem = p.total - t_off;
+        t = t_off + rem * cluster_id / num_clusters;
+        t_end = t_off + rem * (cluster_id + 1) / num_clusters;
+    }
+    FLITE_DEVICE bool next(int& u, int& j0, int& j1) {
+        if (u_rr < rr_units) { u = (int)u_rr; j0 = 0; j1 = NT; u_rr += C; return true; }
+        if (t >= t_end) return false;
+        u = (int)(t / NT); j0 = (int)(t - (long long)u * NT);
+        j1 = (int)min((long long)NT, j0 + (t_end - t));
+        t += j1 - j0;
+        return true;
+    }
+};
+
+constexpr int SK_THREADS = 192;
+
+__global__ void __launch_bounds__(SK_THREADS, 1)
 attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-               const __grid_constant__ CUtensorMap tmap_v, const AttnSkParams p) {
+               const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+               const AttnSkParams p) {
     pdl_launch_dependents();
     pdl_wait();
     const uint32_t cta_rank = cluster_ctarank();
@@ -113,17 +145,15 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
     const int NT = p.NT;
     const int tail_n = (p.k_len & 127) ? (((p.k_len & 127) + 15) & ~15) : 128;   // MMA extent of a ragged last key tile
-    const long long t_begin = p.total * cluster_id / num_clusters;
-    const long long t_end = p.total * (cluster_id + 1) / num_clusters;
-    // segment walk, identical in every role: for (t = t_begin; t < t_end; t += j1 - j0) { u = t / NT; j0 = t % NT; ... }
+    // segment walk, identical in every role: SkWalk w(p, cluster_id, num_clusters); while (w.next(u, j0, j1)) { ... }
 
     if (warp_idx == 0) {
         // ================================ TMA producer (both CTAs) ================================
         if (elect_one()) {
             int g = 0, seg = 0;
-            for (long long t = t_begin; t < t_end; ++seg) {
-                const int u = (int)(t / NT), j0 = (int)(t - (long long)u * NT);
-                const int j1 = (int)min((long long)NT, j0 + (t_end - t));
+            SkWalk w(p, cluster_id, num_clusters);
+            int u, j0, j1;
+            for (; w.next(u, j0, j1); ++seg) {
                 const int qt = u % p.QT, bh = u / p.QT, h = bh % p.H, b = bh / p.H;
                 const int q_row0 = p.cu_q[b] + qt * 256 + (int)cta_rank * 128;
                 const int k_beg = p.cu_k[b];
@@ -150,7 +180,6 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         tma_load_2d_cg2(smem + ATT2_SV + st * 32768 + c * 16384, &tmap_v, &v_full[st], 0,
                                         p.v_col0 + h * 256 + (int)cta_rank * 128 + c * 64, krow);
                 }
-                t += j1 - j0;
             }
         }
         __syncwarp();
@@ -162,9 +191,9 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             constexpr uint32_t idesc_o = make_idesc_bf16(256, 256, 0, 1);
             const uint32_t sq = smem_u32(smem + ATT2_SQ), sk = smem_u32(smem + ATT2_SK), sv = smem_u32(smem + ATT2_SV);
             int g0 = 0, seg = 0;
-            for (long long t = t_begin; t < t_end; ++seg) {
-                const int u = (int)(t / NT), j0 = (int)(t - (long long)u * NT);
-                const int j1 = (int)min((long long)NT, j0 + (t_end - t));
+            SkWalk w(p, cluster_id, num_clusters);
+            int u, j0, j1;
+            for (; w.next(u, j0, j1); ++seg) {
                 const int n = j1 - j0;
                 auto issue_s = [&](int i) {      // S of the segment's i-th tile
                     const int g = g0 + i, j = j0 + i, st = g & 1;
@@ -204,7 +233,6 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     umma_commit_cg2(pv_done, 0x3);
                 }
                 g0 += n;
-                t += n;
             }
         }
         __syncwarp();
@@ -215,9 +243,9 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int r = q * 32 + lane;                         // row inside this CTA's 128-query tile
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         int g0 = 0;
-        for (long long t = t_begin; t < t_end;) {
-            const int u = (int)(t / NT), j0 = (int)(t - (long long)u * NT);
-            const int j1 = (int)min((long long)NT, j0 + (t_end - t));
+        SkWalk w(p, cluster_id, num_clusters);
+        int u, j0, j1;
+        while (w.next(u, j0, j1)) {
             const int n = j1 - j0;
             const int qt = u % p.QT, bh = u / p.QT, h = bh % p.H, b = bh / p.H;
             float m_used = -INFINITY, l = 0.f;
@@ -421,15 +449,51 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 emit_rows(w1, w2, prow);
                 named_bar_sync(1, 128);                // every row of this CTA has consumed the partial
                 if (r == 0) *const_cast<volatile unsigned int*>(f) = 0u;   // idle again (graph replay / next launch)
+            } else if (p.debug & 8) {
+            } else if (p.tma_out && p.out_peer[0] == nullptr && qt * 256 + (int)cta_rank * 128 + 128 <= p.q_len) {
+                // Whole tile: O / l -> bf16 -> the P region of shared memory (unused: P lives in TMEM) as [128 rows x 64
+                // columns] boxes with the tensor map's 128-byte swizzle, two passes of 128 columns; lane 0 of warp 2 issues the
+                // TMA stores (and owns their bulk groups).  The per-thread row stores of emit_rows touch 32 different cache
+                // lines per instruction (~8k cycles per unit); these are conflict-free st.shared + four bulk stores.
+                const float inv_l = 1.0f / l;
+                const bool issuer = warp_idx == 2 && lane == 0;
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    if (issuer) tma_store_wait_read<0>();            // the previous stores have read the staging region
+                    named_bar_sync(2, 128);
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t o[32];
+                        tmem_ld_x32(tmem_o + lane_off + pass * 128 + c * 32, o);
+                        tmem_ld_wait();
+                        uint8_t* box = smem + ATT2_SP + (c >> 1) * 16384 + r * 128;
+                        const int ch0 = (c & 1) * 4;
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+                            *reinterpret_cast<uint4*>(box + (((ch0 + x) ^ (r & 7)) << 4)) = make_uint4(
+                                pack_bf16x2(__uint_as_float(o[8 * x]) * inv_l, __uint_as_float(o[8 * x + 1]) * inv_l),
+                                pack_bf16x2(__uint_as_float(o[8 * x + 2]) * inv_l, __uint_as_float(o[8 * x + 3]) * inv_l),
+                                pack_bf16x2(__uint_as_float(o[8 * x + 4]) * inv_l, __uint_as_float(o[8 * x + 5]) * inv_l),
+                                pack_bf16x2(__uint_as_float(o[8 * x + 6]) * inv_l, __uint_as_float(o[8 * x + 7]) * inv_l));
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(2, 128);
+                    if (issuer) {
+                        const int row0 = p.cu_q[b] + qt * 256 + (int)cta_rank * 128;
+                        tma_store_2d(&tmap_o, smem + ATT2_SP, h * 256 + pass * 128, row0);
+                        tma_store_2d(&tmap_o, smem + ATT2_SP + 16384, h * 256 + pass * 128 + 64, row0);
+                        tma_store_commit();
+                    }
+                }
             } else {
                 emit_rows(1.0f / l, 0.f, nullptr);
             }
             tc_fence_before();     // this segment's TMEM reads are ordered before the p_full arrival of the next one
             g0 += n;
-            t += n;
         }
     }
 
+    if (warp_idx == 2 && lane_id() == 0) tma_store_wait_read<0>();   // shared memory stays valid until the bulk stores have read it
     tc_fence_before();
     cluster_sync_all();
     if (warp_idx == 1) tmem_dealloc<2>(tmem_base, 512);

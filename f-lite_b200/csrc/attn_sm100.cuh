@@ -35,6 +35,10 @@ struct AttnParams {
     int sp_lq;
     int sp_head0;
     int stage_out;          // attn_fwd_cg2_kernel: 1 = store whole output rows via a shared-memory transpose
+    // attn_fwd_cg2_kernel: 1 = a CTA whose 128 query rows are all valid writes its O tile as bf16 into the (dead) Q region
+    // of shared memory, 128B-swizzled, and one thread sends it out with four TMA box stores: the per-thread row stores of
+    // the plain epilogue are 32 different cache lines per instruction and cost ~8k cycles per unit (ncu: 6 % of the launch)
+    int tma_out;
 };
 
 constexpr int ATT_SQ = 0, ATT_SK = 65536, ATT_SV = 131072, ATT_SP = 196608, ATT_BAR = 229376;

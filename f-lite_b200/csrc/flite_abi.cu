@@ -674,7 +674,7 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
     for (int i = 0; i < 8; ++i) p.out_peer[i] = nullptr;
     p.sp_lq = 1; p.sp_head0 = 0;
     if (peers) {
-        if (variant < FLITE_ATTN_2CTA_1WG || variant > FLITE_ATTN_2CTA_2WG_PTMEM)
+        if (!cg2)
             return fail(FLITE_ERR_INVALID, "attention: the peer-memory output path needs a 2-CTA variant (3..6)");
         if (peers->n <= 0 || peers->n > 8 || peers->lq <= 0) return fail(FLITE_ERR_INVALID, "attention: bad peer table");
         for (int i = 0; i < peers->n; ++i) {
@@ -684,6 +684,7 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
         p.sp_lq = peers->lq; p.sp_head0 = peers->head0;
     }
     p.stage_out = (peers != nullptr || g_tuning[FLITE_TUNE_ATTN_STAGED_STORES]) ? 1 : 0;
+    p.tma_out = (cg2 && !p.stage_out && g_tuning[FLITE_TUNE_ATTN_TMA_OUT] == 0) ? 1 : 0;
     const int q_tiles = (max_q + 127) / 128;
     if (variant == FLITE_ATTN_XRES) {
         // persistent cross-attention with resident K/V: every sequence must have <= 256 keys (checked in the kernel)
@@ -758,6 +759,15 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
         LAUNCH_CHECK();
         return 0;
     }
+    // output tile stores through TMA (whole 128-row tiles only; the map covers exactly the H heads the kernel writes)
+    CUtensorMap to = tq;
+    if (p.tma_out) {
+        if (((uintptr_t)out & 15) != 0) p.tma_out = 0;
+        else {
+            rc = make_tmap(&to, out, (uint64_t)rows_q, (uint64_t)(256ll * H), (uint64_t)ldo, 128);
+            if (rc) return rc;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * ((q_tiles + 1) / 2), H, B);
     const bool one_wg = variant == FLITE_ATTN_2CTA_1WG || variant == FLITE_ATTN_2CTA_1WG_PTMEM;
@@ -768,10 +778,10 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
     cfg.attrs = attr;
     cfg.numAttrs = fill_launch_attrs(attr, 2);
     switch (variant) {
-        case FLITE_ATTN_2CTA_1WG: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<1, false>, tq, tk, tv, p)); break;
-        case FLITE_ATTN_2CTA_2WG: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<2, false>, tq, tk, tv, p)); break;
-        case FLITE_ATTN_2CTA_1WG_PTMEM: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<1, true>, tq, tk, tv, p)); break;
-        default: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<2, true>, tq, tk, tv, p)); break;
+        case FLITE_ATTN_2CTA_1WG: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<1, false>, tq, tk, tv, to, p)); break;
+        case FLITE_ATTN_2CTA_2WG: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<2, false>, tq, tk, tv, to, p)); break;
+        case FLITE_ATTN_2CTA_1WG_PTMEM: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<1, true>, tq, tk, tv, to, p)); break;
+        default: CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_cg2_kernel<2, true>, tq, tk, tv, to, p)); break;
     }
     return 0;
 }
@@ -794,7 +804,7 @@ static int sk_clusters() {
         cudaFuncSetAttribute(attn_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(num_sms() / 2 * 2);
-        cfg.blockDim = dim3(192);
+        cfg.blockDim = dim3(SK_THREADS);
         cfg.dynamicSmemBytes = ATT_SMEM;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -864,15 +874,30 @@ static int attention_streamk_impl(const void* q, int64_t ldq, int64_t rows_q, in
     }
     long long clusters = sk_clusters();
     if (clusters > units) clusters = units;     // a share is never shorter than one unit => a unit has at most two parts
+    // schedule (FLITE_TUNE_ATTN_SK_MODE): 0 pure stream-K | 1 whole units round-robin (never splits: bit-identical to the
+    // one-cluster-per-unit launch) | 2 hybrid: whole rounds in lock step, stream-K shares of 1..2 units over the rest
+    p.rr_units = 0;
+    p.debug = g_tuning[FLITE_TUNE_ATTN_DEBUG];
+    CUtensorMap to = tq;
+    p.tma_out = (!peer_out && g_tuning[FLITE_TUNE_ATTN_TMA_OUT] == 0 && ((uintptr_t)out & 15) == 0) ? 1 : 0;
+    if (p.tma_out) {
+        rc = make_tmap(&to, out, (uint64_t)rows_q, (uint64_t)(256ll * H), (uint64_t)ldo, 128);
+        if (rc) return rc;
+    }
+    if (g_tuning[FLITE_TUNE_ATTN_SK_MODE] == 1) p.rr_units = units;
+    else if (g_tuning[FLITE_TUNE_ATTN_SK_MODE] == 2) {
+        const long long rounds = units / clusters;
+        p.rr_units = (units % clusters == 0) ? units : (rounds >= 1 ? (rounds - 1) * clusters : 0);
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * clusters));
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(SK_THREADS);
     cfg.dynamicSmemBytes = ATT_SMEM;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
     cfg.numAttrs = fill_launch_attrs(attr, 2);
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_sk_kernel, tq, tk, tv, p));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_sk_kernel, tq, tk, tv, to, p));
     return 0;
 }
 

@@ -27,7 +27,7 @@ from typing import Optional
 import torch
 from torch import nn
 
-from . import ops
+from . import _lib, ops
 from ._lib import (ATTN_XRES, EPI_GATED_RES, EPI_QKV_ROPE, EPI_STORE, EPI_SWIGLU, GEMM_AUTO, FliteError)
 
 N_REGISTER = 16  # model.py:446,535,540
@@ -182,15 +182,21 @@ class DiT(nn.Module):
         self._ctx_cache = None
         self._freqs = None
         self.hoist_context = True
-        # Self-attention as one persistent stream-K wave (flite_attention_streamk) instead of one cluster per query tile.
-        # OFF by default: (1) a unit split between two clusters is merged in fp32, so the result depends on where the
-        # shares fall, i.e. on the batch size / head count -- the default path is batch-invariant, which is what makes
-        # the multi-GPU layouts bit-identical to the 1-GPU path; (2) measured (profiles/r2_attn_bench.json): it loses
-        # 8 % at C2 (the 74 clusters no longer walk the same key tiles in lock step, so K/V tiles stop being shared in
-        # L2), wins 1 % at C4 and 9 % on a sequence-parallel rank's 3 heads x 16400 tokens (390 units = 5.27 waves).
-        # "auto" (FLITE_ATTN_STREAMK=auto) turns it on when the per-tile grid wastes >= 10 % of its last wave on long
-        # sequences; "1" forces it.
-        self.attn_streamk = os.environ.get("FLITE_ATTN_STREAMK", "0")
+        # Self-attention schedule (every image sequence has the same length, so the persistent kernel applies):
+        #   "rr" (default)  flite_attention_streamk with whole 256-query units handed out round-robin to ONE wave of
+        #                   clusters: no unit is ever split, so the result is bit-identical to the one-cluster-per-unit launch
+        #                   and batch-invariant (which is what keeps the multi-GPU layouts bit-identical to the 1-GPU path);
+        #                   barrier init / TMEM allocation happen once and the next unit's Q / K loads start under the
+        #                   previous unit's tail.  Measured (profiles/r2x_attn_probe.json, r2x_ab_step_c2.json): +3.4 % on the
+        #                   C2 launch, +4.7 % at C5, 0.7 ms off the C2 step.
+        #   "0"             one cluster per unit (flite_attention_varlen), the round-1 path.
+        #   "1" / "auto"    stream-K shares: a unit split between two clusters is merged in fp32, so the result depends on
+        #                   where the shares fall (batch size / head count); loses 8 % at C2 (the clusters no longer walk the
+        #                   same key tiles in lock step: 1.0 GB of DRAM reads per launch instead of 0.15), wins on a
+        #                   sequence-parallel rank's 3 heads x 16400 tokens.  "auto" picks it when the per-unit grid wastes
+        #                   >= 10 % of its last wave on long sequences.
+        #   "hybrid"        whole rounds in lock step, stream-K shares over the last 1..2 units per cluster.
+        self.attn_streamk = os.environ.get("FLITE_ATTN_STREAMK", "rr")
         self.gemm_variant = GEMM_AUTO
         self.sp_group = None      # Ulysses sequence-parallel process group (see enable_sequence_parallel)
         self.sp_fused = False     # exchanges fused into the kernels over NVLink peer memory instead of NCCL
@@ -241,6 +247,10 @@ class DiT(nn.Module):
 
     def _use_streamk(self, B, heads, L):
         mode = self.attn_streamk
+        if mode in ("rr", "hybrid"):
+            _lib.load().flite_set_tuning(15, 1 if mode == "rr" else 2)
+            return True
+        _lib.load().flite_set_tuning(15, 0)
         if mode in (True, "1", 1):
             return True
         if mode != "auto":

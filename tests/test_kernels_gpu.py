@@ -391,7 +391,8 @@ def test_fused_ulysses_kernels_single_gpu_loopback(P):
         assert torch.equal(a_, b_)
 
 
-def test_attention_streamk_peer_epilogue_with_split_units():
+@pytest.mark.parametrize("sk_mode", [0, 1, 2], indirect=True)
+def test_attention_streamk_peer_epilogue_with_split_units(sk_mode):
     """Stream-K attention with the staged peer-store epilogue at a size where units ARE split between clusters
     (2 x 4 heads x 5 query tiles = 40 units... 12 heads: 120 units > 74 clusters): the rows written through the peer table
     (all "peers" on this GPU) must equal the locally stored result of the same kernel."""
@@ -647,13 +648,26 @@ def test_gemm_narrow_last_m_tile_bit_equal(M):
     assert rel(narrow[0][:M], F.linear(a, w, bias)) <= 1e-3
 
 
+@pytest.fixture
+def sk_mode(request):
+    """schedule of the persistent attention kernel (FLITE_TUNE_ATTN_SK_MODE): 0 stream-K, 1 whole units round-robin, 2 hybrid"""
+    from flite_b200 import _lib
+    lib = _lib.load()
+    old = lib.flite_get_tuning(15)
+    lib.flite_set_tuning(15, request.param)
+    yield request.param
+    lib.flite_set_tuning(15, old)
+
+
+@pytest.mark.parametrize("sk_mode", [0, 1, 2], indirect=True)
 @pytest.mark.parametrize("B,H,Lq,Lk", [(2, 12, 4112, 4112), (4, 12, 600, 600), (2, 12, 1024, 300), (2, 2, 272, 272),
-                                       (3, 4, 1000, 129), (1, 3, 16400, 16400)])
-def test_attention_streamk_matches_general_kernel(B, H, Lq, Lk):
-    """flite_attention_streamk (persistent stream-K wave, uniform lengths) vs flite_attention_varlen (one cluster per
-    256-query tile): units that one cluster computes alone give the same bits; a unit split between two clusters is
-    merged in fp32, so it may differ by a bf16 ulp.  Also vs the fp32 oracle, and a second launch must reproduce the
-    first bit for bit (the merge flags are reset by their reader)."""
+                                       (3, 4, 1000, 129), (1, 3, 16400, 16400), (8, 12, 4112, 4112)])
+def test_attention_streamk_matches_general_kernel(B, H, Lq, Lk, sk_mode):
+    """flite_attention_streamk (persistent wave of clusters, uniform lengths; unit read-out on the epilogue warps) vs
+    flite_attention_varlen (one cluster per 256-query tile): units that one cluster computes alone give the same bits --
+    in the round-robin schedule (mode 1) that is every unit; a unit split between two clusters (stream-K shares, modes 0
+    and 2) is merged in fp32, so it may differ by a bf16 ulp.  Also vs the fp32 oracle, and a second launch must
+    reproduce the first bit for bit (the merge flags are reset by their reader)."""
     from flite_b200 import ops
     from oracle import dit_oracle
     d = H * 256
@@ -676,8 +690,10 @@ def test_attention_streamk_matches_general_kernel(B, H, Lq, Lk):
     assert torch.equal(out[:B * Lq], again)
     eq = (out[:B * Lq] == base).float().mean().item()
     r = rel(out[:B * Lq], base)
-    print(f"streamk vs general: bit-equal {eq:.4f} rel {r:.2e}")
+    print(f"streamk (mode {sk_mode}) vs general: bit-equal {eq:.4f} rel {r:.2e}")
     assert r <= 2e-3 and eq > 0.5
+    if sk_mode == 1:
+        assert torch.equal(out[:B * Lq], base)
     if B * Lq * Lk * H <= 2 * 12 * 4112 * 4112:
         ref = dit_oracle.flash_attn_varlen(q.view(-1, H, 256).float(), k.view(-1, H, 256).float(),
                                            v.view(-1, H, 256).float(), cu_q, cu_k, scale).reshape(-1, d)

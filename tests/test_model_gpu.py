@@ -534,9 +534,13 @@ def test_batch4_per_gpu_layout_is_bit_identical_to_per_image_runs():
     t = torch.full((2 * b,), 0.6, device=DEV).bfloat16()
     x2, c2 = torch.cat([lat, lat]), torch.cat([neg, pos])
     v0 = m(x2, c2, mask, t)
-    m.attn_streamk = "1"
+    default = m.attn_streamk
     try:
-        v1 = m(x2, c2, mask, t)
+        m.attn_streamk = "0"                 # one cluster per unit: the round-robin default must reproduce it bit for bit
+        assert torch.equal(m(x2, c2, mask, t), v0)
+        for mode in ("1", "hybrid"):         # stream-K shares: split units are merged in fp32
+            m.attn_streamk = mode
+            assert rel(m(x2, c2, mask, t), v0) <= TOL
     finally:
-        m.attn_streamk = "0"
-    assert rel(v1, v0) <= TOL
+        m.attn_streamk = default
+    assert default == "rr"
