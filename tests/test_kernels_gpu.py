@@ -429,6 +429,31 @@ def test_p2p_flags_signal_then_wait_loopback():
 
 
 @pytest.mark.parametrize("variant", [3, 4, 5, 6])
+def test_attention_tma_store_epilogue_bit_equal(variant):
+    """FLITE_TUNE_ATTN_TMA_OUT: whole 128-row output tiles leave through shared memory + TMA bulk stores (default); ragged
+    last tiles, single-row and empty-key sequences keep the per-thread path.  Same bits as with the TMA path switched off,
+    nothing written outside the rows of the call, and a column-offset / strided output view works."""
+    from flite_b200 import _lib, ops
+    H = 2
+    q_lens, k_lens = [300, 1, 272, 512], [129, 0, 272, 40]
+    cu_q = torch.tensor([0] + list(np.cumsum(q_lens)), dtype=torch.int32, device=DEV)
+    cu_k = torch.tensor([0] + list(np.cumsum(k_lens)), dtype=torch.int32, device=DEV)
+    nq = sum(q_lens)
+    q, k, v = rnd(nq, H * 256, seed=1), rnd(sum(k_lens), H * 256, seed=2), rnd(sum(k_lens), H * 256, seed=3)
+    lib = _lib.load()
+    wide = torch.full((nq + 4, H * 256 + 64), 7.0, device=DEV, dtype=torch.bfloat16)     # strided view, 16-byte aligned
+    ops.attention_varlen(q, k, v, cu_q, cu_k, H, max(q_lens), 1 / 16, variant=variant, out=wide[:nq, 64:])
+    lib.flite_set_tuning(16, 1)
+    try:
+        rows = ops.attention_varlen(q, k, v, cu_q, cu_k, H, max(q_lens), 1 / 16, variant=variant)
+    finally:
+        lib.flite_set_tuning(16, 0)
+    _lib.watchdog_ok()
+    assert torch.equal(wide[:nq, 64:], rows)
+    assert bool((wide[nq:] == 7.0).all()) and bool((wide[:, :64] == 7.0).all())
+
+
+@pytest.mark.parametrize("variant", [3, 4, 5, 6])
 def test_attention_staged_output_stores_bit_equal(variant):
     """FLITE_TUNE_ATTN_STAGED_STORES: whole-row output stores through the dead Q tile give the same bits as the
     one-row-per-thread stores; ragged query tails and an empty key sequence included."""
