@@ -201,6 +201,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
         };
         p.hint_a = policy(g_tuning[FLITE_TUNE_GEMM_HINT_A]);
         p.hint_b = policy(g_tuning[FLITE_TUNE_GEMM_HINT_B]);
+        p.debug = g_tuning[FLITE_TUNE_GEMM_DEBUG];
         // narrow last M-tile (<= 128 valid rows of the 256): M = 128 MMAs, half the padding cost.  Not for the QKV epilogue
         // (needs a whole head per thread pair), and only when the first band (which holds the narrow tile) is made of
         // whole-width units.

@@ -75,6 +75,7 @@ extern "C" {
 #define FLITE_TUNE_GEMM_NARROW_M 14    /* 0 = a last M-tile with <= 128 valid rows runs as M = 128 MMAs (default), 1 = padded 256-row tile */
 #define FLITE_TUNE_ATTN_SK_MODE 15     /* schedule of flite_attention_streamk: 0 = stream-K shares | 1 = whole units round-robin (persistent, never splits a unit) | 2 = hybrid (whole rounds in lock step, stream-K over the last 1..2 units per cluster) */
 #define FLITE_TUNE_ATTN_TMA_OUT 16     /* 0 = the 2-CTA attention kernels store whole 128-row output tiles through shared memory + TMA (default), 1 = per-thread row stores */
+#define FLITE_TUNE_GEMM_DEBUG 17       /* profiling experiments only: bit0 = gated-residual epilogue without its global loads / stores */
 #define FLITE_TUNE_GEMM_BAND 5       /* 0 = L2-aware band rasterisation for large M (default), 1 = single band */
 int flite_set_tuning(int key, int value);
 int flite_get_tuning(int key);   /* current value of a knob (0 for an unknown key) */
