@@ -31,8 +31,16 @@ if which in ("attn", "all"):
     cu = torch.arange(3, device=dev, dtype=torch.int32) * (T // 2)
     o = torch.empty(T, d, device=dev, dtype=torch.bfloat16)
     var = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    for _ in range(REP):
+    for _ in range(REP):     # one cluster per 256-query unit
         ops.attention_varlen(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, 12, T // 2, 256 ** -0.5, out=o, variant=var)
+    _lib.load().flite_set_tuning(15, 1)
+    for _ in range(REP):     # the DiT's default self-attention path: persistent kernel, whole units round-robin
+        ops.attention_streamk(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, 12, T // 2, T // 2, 256 ** -0.5, out=o)
+    _lib.load().flite_set_tuning(15, 0)
+    ctx_kv = torch.randn(512, 2 * d, device=dev).bfloat16()      # cross-attention: 2 x 256 text keys
+    cuk = torch.arange(3, device=dev, dtype=torch.int32) * 256
+    for _ in range(REP):
+        ops.attention_varlen(qkv[:, :d], ctx_kv[:, :d], ctx_kv[:, d:], cu, cuk, 12, T // 2, 256 ** -0.5, out=o)
 if which in ("norm", "all"):
     x = torch.randn(T, d, device=dev).bfloat16(); w = torch.ones(d, device=dev).bfloat16()
     mod = torch.randn(2, 9 * d, device=dev).bfloat16(); y = torch.empty_like(x)
