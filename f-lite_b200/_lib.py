@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libflite_b200.so")
 FLITE_OK = 0
 EPI_STORE, EPI_GATED_RES, EPI_SWIGLU, EPI_QKV_ROPE = 0, 1, 2, 3
 GEMM_AUTO, GEMM_1CTA_N256, GEMM_2CTA_N256, GEMM_1CTA_N128, GEMM_1CTA_N64, GEMM_GEMV = 0, 1, 2, 3, 4, 5
-ATTN_AUTO, ATTN_1WG, ATTN_2WG, ATTN_2CTA_1WG, ATTN_2CTA_2WG, ATTN_2CTA_1WG_PTMEM, ATTN_2CTA_2WG_PTMEM, ATTN_QTMEM_1WG, ATTN_QTMEM_2WG, ATTN_XRES = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+ATTN_AUTO, ATTN_1WG, ATTN_2WG, ATTN_2CTA_1WG, ATTN_2CTA_2WG, ATTN_2CTA_1WG_PTMEM, ATTN_2CTA_2WG_PTMEM, ATTN_QTMEM_1WG, ATTN_QTMEM_2WG, ATTN_XRES, ATTN_PERSISTENT = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 
 _P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
 

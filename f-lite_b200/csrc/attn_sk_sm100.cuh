@@ -45,6 +45,10 @@ struct AttnSkParams {
     long long rr_units;
     int debug;             // profiling experiments only (0 in production): bit3 = skip the epilogue of whole units
     int tma_out;           // 1 = whole units with 128 valid rows per CTA leave through shared memory + TMA box stores
+    // ragged = 1 (round-robin schedule only: rr_units == all units): per-sequence query / key lengths from cu_q / cu_k, QT =
+    // query tiles of the LONGEST sequence (units past a sequence's end are skipped), an empty key sequence gives zeros.
+    // This is the cross-attention over the packed text context (f_lite/model.py:188-210) on the persistent kernel.
+    int ragged;
     unsigned int* flags;   // workspace head: [cluster slot][cta rank], zero when idle
     float* slots;          // workspace body: [cluster slot][SK_SLOT_FLOATS]
     // Fused Ulysses return path (as in attn_fwd_cg2_kernel): when out_peer[0] != nullptr query row l of this rank's heads
@@ -77,6 +81,32 @@ struct SkWalk {
     }
 };
 
+// What one segment works on.  Uniform mode: every sequence has p.q_len / p.k_len tokens and [j0, j1) comes from the walk;
+// ragged mode: the lengths of sequence b, whole units only ([0, nt)).  active == false: no MMA / load / barrier traffic at all
+// (no query rows here, or no keys: the softmax warps then write zeros).
+struct SkSeg {
+    int b, h, qt, q_beg, q_len, k_beg, k_len, nt, tail_n;
+    bool active;
+};
+FLITE_DEVICE SkSeg sk_segment(const AttnSkParams& p, int u, int& j0, int& j1) {
+    SkSeg s;
+    s.qt = u % p.QT;
+    const int bh = u / p.QT;
+    s.h = bh % p.H; s.b = bh / p.H;
+    s.q_beg = p.cu_q[s.b]; s.k_beg = p.cu_k[s.b];
+    if (p.ragged) {
+        s.q_len = p.cu_q[s.b + 1] - s.q_beg;
+        s.k_len = p.cu_k[s.b + 1] - s.k_beg;
+    } else {
+        s.q_len = p.q_len; s.k_len = p.k_len;
+    }
+    s.nt = (s.k_len + 127) / 128;
+    s.tail_n = (s.k_len & 127) ? (((s.k_len & 127) + 15) & ~15) : 128;   // MMA extent of a ragged last key tile
+    if (p.ragged) { j0 = 0; j1 = s.nt; }
+    s.active = s.qt * 256 < s.q_len && j1 > j0;
+    return s;
+}
+
 constexpr int SK_THREADS = 192;
 
 __global__ void __launch_bounds__(SK_THREADS, 1)
@@ -94,8 +124,12 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     // preconditions, same answer in every thread of every CTA, before any barrier: smem window, uniform lengths
     {
         bool bad = (smem - smem_raw) + ATT_SMEM_USED > ATT_SMEM;
-        for (int b = 0; b < p.B; ++b)
-            bad |= (p.cu_q[b + 1] - p.cu_q[b] != p.q_len) || (p.cu_k[b + 1] - p.cu_k[b] != p.k_len);
+        if (!p.ragged) {
+            for (int b = 0; b < p.B; ++b)
+                bad |= (p.cu_q[b + 1] - p.cu_q[b] != p.q_len) || (p.cu_k[b + 1] - p.cu_k[b] != p.k_len);
+        } else {
+            bad |= p.rr_units * p.NT != p.total;     // ragged lengths: whole units only
+        }
         if (bad) {
             if (threadIdx.x == 0) atomicCAS(&g_flite_abort, 0u, (95u << 16) | 0x80000000u);
             return;
@@ -143,8 +177,6 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const uint32_t tmem_base = *tmem_ptr_smem;
     const uint32_t tmem_o = tmem_base + 256;
 
-    const int NT = p.NT;
-    const int tail_n = (p.k_len & 127) ? (((p.k_len & 127) + 15) & ~15) : 128;   // MMA extent of a ragged last key tile
     // segment walk, identical in every role: SkWalk w(p, cluster_id, num_clusters); while (w.next(u, j0, j1)) { ... }
 
     if (warp_idx == 0) {
@@ -153,10 +185,11 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             int g = 0, seg = 0;
             SkWalk w(p, cluster_id, num_clusters);
             int u, j0, j1;
-            for (; w.next(u, j0, j1); ++seg) {
-                const int qt = u % p.QT, bh = u / p.QT, h = bh % p.H, b = bh / p.H;
-                const int q_row0 = p.cu_q[b] + qt * 256 + (int)cta_rank * 128;
-                const int k_beg = p.cu_k[b];
+            for (; w.next(u, j0, j1);) {
+                const SkSeg sg = sk_segment(p, u, j0, j1);
+                if (!sg.active) continue;
+                const int h = sg.h, k_beg = sg.k_beg, NT = sg.nt, tail_n = sg.tail_n;
+                const int q_row0 = sg.q_beg + sg.qt * 256 + (int)cta_rank * 128;
                 if (seg > 0) mbar_wait<true>(q_empty, (seg - 1) & 1, 41);
                 if (is_leader) mbar_arrive_expect_tx(q_full, 2 * 65536);
 #pragma unroll
@@ -180,6 +213,7 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         tma_load_2d_cg2(smem + ATT2_SV + st * 32768 + c * 16384, &tmap_v, &v_full[st], 0,
                                         p.v_col0 + h * 256 + (int)cta_rank * 128 + c * 64, krow);
                 }
+                ++seg;
             }
         }
         __syncwarp();
@@ -187,14 +221,16 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // ================================ MMA issuer (leader CTA) ================================
         if (is_leader && elect_one()) {
             constexpr uint32_t idesc_s_full = make_idesc_bf16(256, 128, 0, 0);
-            const uint32_t idesc_s_tail = make_idesc_bf16(256, tail_n, 0, 0);
             constexpr uint32_t idesc_o = make_idesc_bf16(256, 256, 0, 1);
             const uint32_t sq = smem_u32(smem + ATT2_SQ), sk = smem_u32(smem + ATT2_SK), sv = smem_u32(smem + ATT2_SV);
             int g0 = 0, seg = 0;
             SkWalk w(p, cluster_id, num_clusters);
             int u, j0, j1;
-            for (; w.next(u, j0, j1); ++seg) {
-                const int n = j1 - j0;
+            for (; w.next(u, j0, j1);) {
+                const SkSeg sg = sk_segment(p, u, j0, j1);
+                if (!sg.active) continue;
+                const int n = j1 - j0, NT = sg.nt, tail_n = sg.tail_n;
+                const uint32_t idesc_s_tail = make_idesc_bf16(256, tail_n, 0, 0);
                 auto issue_s = [&](int i) {      // S of the segment's i-th tile
                     const int g = g0 + i, j = j0 + i, st = g & 1;
                     mbar_wait<true>(&k_full[st], (g >> 1) & 1, 44);
@@ -233,6 +269,7 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     umma_commit_cg2(pv_done, 0x3);
                 }
                 g0 += n;
+                ++seg;
             }
         }
         __syncwarp();
@@ -246,15 +283,26 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         SkWalk w(p, cluster_id, num_clusters);
         int u, j0, j1;
         while (w.next(u, j0, j1)) {
+            const SkSeg sg = sk_segment(p, u, j0, j1);
+            const int qt = sg.qt, h = sg.h, b = sg.b, NT = sg.nt;
+            if (!sg.active) {
+                // no keys (ragged mode): flash-attn returns zeros for the rows that exist; no rows: nothing to do
+                const int row_in_seq0 = qt * 256 + (int)cta_rank * 128 + r;
+                if (row_in_seq0 < sg.q_len) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)(sg.q_beg + row_in_seq0) * p.ldo + h * 256);
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) dst[x] = make_uint4(0, 0, 0, 0);
+                }
+                continue;
+            }
             const int n = j1 - j0;
-            const int qt = u % p.QT, bh = u / p.QT, h = bh % p.H, b = bh / p.H;
             float m_used = -INFINITY, l = 0.f;
             for (int i = 0; i < n; ++i) {
                 const int g = g0 + i, j = j0 + i;
                 mbar_wait<true>(&s_full[g & 1], (g >> 1) & 1, 48);
                 tc_fence_after();
                 const uint32_t ts = tmem_base + lane_off + (g & 1) * 128;
-                const int kv_valid = min(128, p.k_len - j * 128);
+                const int kv_valid = min(128, sg.k_len - j * 128);
                 const bool full = kv_valid >= 128;
                 uint32_t s[128];
 #pragma unroll
@@ -333,13 +381,13 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             mbar_wait<true>(pv_done, (g0 + n - 1) & 1, 50);
             tc_fence_after();
             const int row_in_seq = qt * 256 + (int)cta_rank * 128 + r;
-            const bool row_ok = row_in_seq < p.q_len;
+            const bool row_ok = row_in_seq < sg.q_len;
             const bool is_writer = j0 > 0;             // this cluster owns the unit's LAST key tiles: publish a partial
             const bool is_reader = j1 < NT;            // ... the FIRST key tiles: merge the partner's partial and finish
             // final rows of this unit: out = O * w1 (+ partner partial * w2), bf16; local rows are stored directly, rows
             // that belong to a peer GPU are staged through smem and leave as whole 256-byte segments
             auto emit_rows = [&](float w1, float w2, const float4* prow) {
-                __nv_bfloat16* orow = p.out + (long long)(p.cu_q[b] + row_in_seq) * p.ldo + h * 256;
+                __nv_bfloat16* orow = p.out + (long long)(sg.q_beg + row_in_seq) * p.ldo + h * 256;
                 const bool to_peer = p.out_peer[0] != nullptr;
                 if (to_peer && row_ok) {
                     const int owner = row_in_seq / p.sp_lq, li = row_in_seq - owner * p.sp_lq;
@@ -450,7 +498,7 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 named_bar_sync(1, 128);                // every row of this CTA has consumed the partial
                 if (r == 0) *const_cast<volatile unsigned int*>(f) = 0u;   // idle again (graph replay / next launch)
             } else if (p.debug & 8) {
-            } else if (p.tma_out && p.out_peer[0] == nullptr && qt * 256 + (int)cta_rank * 128 + 128 <= p.q_len) {
+            } else if (p.tma_out && p.out_peer[0] == nullptr && qt * 256 + (int)cta_rank * 128 + 128 <= sg.q_len) {
                 // Whole tile: O / l -> bf16 -> the P region of shared memory (unused: P lives in TMEM) as [128 rows x 64
                 // columns] boxes with the tensor map's 128-byte swizzle, two passes of 128 columns; lane 0 of warp 2 issues the
                 // TMA stores (and owns their bulk groups).  The per-thread row stores of emit_rows touch 32 different cache
@@ -479,7 +527,7 @@ attn_sk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                     fence_proxy_async_smem();
                     named_bar_sync(2, 128);
                     if (issuer) {
-                        const int row0 = p.cu_q[b] + qt * 256 + (int)cta_rank * 128;
+                        const int row0 = sg.q_beg + qt * 256 + (int)cta_rank * 128;
                         tma_store_2d(&tmap_o, smem + ATT2_SP, h * 256 + pass * 128, row0);
                         tma_store_2d(&tmap_o, smem + ATT2_SP + 16384, h * 256 + pass * 128 + 64, row0);
                         tma_store_commit();

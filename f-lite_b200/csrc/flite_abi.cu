@@ -630,6 +630,8 @@ struct AttnPeers {
     int n, lq, head0;
 };
 
+static int sk_clusters();
+
 static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
                           int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
                           const int* cu_q, const int* cu_k, int B, int H, int max_q, float softmax_scale,
@@ -657,16 +659,64 @@ static int attention_impl(const void* q, int64_t ldq, int64_t rows_q, int q_col0
         CUDA_TRY(cudaFuncSetAttribute(attn_fwd_qtmem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM));
         configured = true;
     }
-    if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_XRES)
+    if (variant < FLITE_ATTN_AUTO || variant > FLITE_ATTN_PERSISTENT)
         return fail(FLITE_ERR_INVALID, "attention: unknown variant %d", variant);
     // short key sequences (cross-attention over the text context: <= 512 keys per sequence on average) may use their own variant
     if (variant == FLITE_ATTN_AUTO && !peers && rows_k <= 512ll * B && g_tuning[FLITE_TUNE_ATTN_VARIANT_SHORT_K] > 0 &&
         g_tuning[FLITE_TUNE_ATTN_VARIANT_SHORT_K] != FLITE_ATTN_XRES)   // XRES needs the per-sequence bound the host knows
         variant = g_tuning[FLITE_TUNE_ATTN_VARIANT_SHORT_K];
-    if (variant == FLITE_ATTN_AUTO) variant = g_tuning[FLITE_TUNE_ATTN_VARIANT] ? g_tuning[FLITE_TUNE_ATTN_VARIANT] : FLITE_ATTN_2CTA_1WG_PTMEM;
+    // default: the persistent kernel (whole units round-robin over one wave of clusters; bit-identical to variant 5 and
+    // faster at every measured shape: cross-attention 72 -> 48 us at C2, 511 -> 298 us at C3, self-attention 339 -> 323 us);
+    // peer-memory output goes through the per-unit kernel
+    if (variant == FLITE_ATTN_AUTO)
+        variant = g_tuning[FLITE_TUNE_ATTN_VARIANT] ? g_tuning[FLITE_TUNE_ATTN_VARIANT]
+                                                    : (peers ? FLITE_ATTN_2CTA_1WG_PTMEM : FLITE_ATTN_PERSISTENT);
+    if (variant == FLITE_ATTN_PERSISTENT && peers) variant = FLITE_ATTN_2CTA_1WG_PTMEM;   // peer stores: the per-unit kernel
+    if (variant == FLITE_ATTN_PERSISTENT) {
+        // One wave of clusters, whole (sequence, head, 256-query tile) units handed out round-robin, per-sequence lengths
+        // from cu_q / cu_k (attn_sk_kernel, ragged mode): same arithmetic per unit as variant 5, no per-unit launch cost.
+        CUtensorMap tq, tk, tv, to;
+        int rc = make_tmap(&tq, q, (uint64_t)rows_q, (uint64_t)q_cols, (uint64_t)ldq, 128);
+        if (rc) return rc;
+        rc = make_tmap(&tk, k, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)k_cols, (uint64_t)ldk, 64);
+        if (rc) return rc;
+        rc = make_tmap(&tv, v, (uint64_t)(rows_k > 0 ? rows_k : 1), (uint64_t)v_cols, (uint64_t)ldv, 128);
+        if (rc) return rc;
+        AttnSkParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.cu_q = cu_q; sp.cu_k = cu_k;
+        sp.out = (__nv_bfloat16*)out; sp.ldo = ldo;
+        sp.q_col0 = q_col0; sp.k_col0 = k_col0; sp.v_col0 = v_col0;
+        sp.scale_log2 = softmax_scale * 1.4426950408889634f;
+        sp.B = B; sp.H = H;
+        sp.QT = (max_q + 255) / 256; sp.NT = 1;
+        const long long units = (long long)B * H * sp.QT;
+        sp.total = units; sp.rr_units = units; sp.ragged = 1;
+        sp.debug = g_tuning[FLITE_TUNE_ATTN_DEBUG];
+        sp.sp_lq = 1;
+        to = tq;
+        sp.tma_out = (g_tuning[FLITE_TUNE_ATTN_TMA_OUT] == 0 && ((uintptr_t)out & 15) == 0) ? 1 : 0;
+        if (sp.tma_out) {
+            rc = make_tmap(&to, out, (uint64_t)rows_q, (uint64_t)(256ll * H), (uint64_t)ldo, 128);
+            if (rc) return rc;
+        }
+        long long clusters = sk_clusters();
+        if (clusters > units) clusters = units;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * clusters));
+        cfg.blockDim = dim3(SK_THREADS);
+        cfg.dynamicSmemBytes = ATT_SMEM;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[2];
+        cfg.attrs = attr;
+        cfg.numAttrs = fill_launch_attrs(attr, 2);
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_sk_kernel, tq, tk, tv, to, sp));
+        return 0;
+    }
     const bool cg2 = variant >= FLITE_ATTN_2CTA_1WG && variant <= FLITE_ATTN_2CTA_2WG_PTMEM;
     const bool qtmem = variant == FLITE_ATTN_QTMEM_1WG || variant == FLITE_ATTN_QTMEM_2WG;
     AttnParams p;
+    memset(&p, 0, sizeof(p));
     p.cu_q = cu_q; p.cu_k = cu_k;
     p.out = (__nv_bfloat16*)out; p.ldo = ldo;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
@@ -853,6 +903,7 @@ static int attention_streamk_impl(const void* q, int64_t ldq, int64_t rows_q, in
     rc = make_tmap(&tv, v, (uint64_t)rows_k, (uint64_t)v_cols, (uint64_t)ldv, 128);
     if (rc) return rc;
     AttnSkParams p;
+    memset(&p, 0, sizeof(p));
     p.cu_q = cu_q; p.cu_k = cu_k;
     p.out = (__nv_bfloat16*)out; p.ldo = ldo;
     p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;

@@ -189,7 +189,9 @@ class DiT(nn.Module):
         #                   barrier init / TMEM allocation happen once and the next unit's Q / K loads start under the
         #                   previous unit's tail.  Measured (profiles/r2x_attn_probe.json, r2x_ab_step_c2.json): +3.4 % on the
         #                   C2 launch, +4.7 % at C5, 0.7 ms off the C2 step.
-        #   "0"             one cluster per unit (flite_attention_varlen), the round-1 path.
+        #   "0"             flite_attention_varlen with FLITE_ATTN_AUTO: the same persistent kernel in its ragged-length
+        #                   mode (what the cross-attention calls use); FLITE_TUNE_ATTN_VARIANT = 5 selects the round-1 path,
+        #                   one cluster per unit.
         #   "1" / "auto"    stream-K shares: a unit split between two clusters is merged in fp32, so the result depends on
         #                   where the shares fall (batch size / head count); loses 8 % at C2 (the clusters no longer walk the
         #                   same key tiles in lock step: 1.0 GB of DRAM reads per launch instead of 0.15), wins on a
@@ -501,9 +503,10 @@ class DiT(nn.Module):
             ao_full = self._buf("ao_full", (B, L, dq), dev)
             ao_recv = self._buf("ao_recv", (B, P, Lq * dq), dev)         # [sample][source rank][local token, head group]
 
-        # cross-attention over <= 256 context tokens per sequence may use the persistent resident-K/V kernel
-        # (FLITE_ATTN_XRES): opt-in through FLITE_TUNE_ATTN_VARIANT_SHORT_K = 9 -- 10-15 % faster than the general kernel
-        # on that launch (0.17 ms of a 104 ms step at C2), parity-tested in tests/test_kernels_gpu.py.
+        # Cross-attention goes through flite_attention_varlen with FLITE_ATTN_AUTO = the persistent kernel with per-sequence
+        # key lengths (72 -> 48 us per launch at C2, bit-identical to the per-unit kernel).  The round-1 resident-K/V kernel
+        # (FLITE_ATTN_XRES, <= 256 context tokens) stays selectable through FLITE_TUNE_ATTN_VARIANT_SHORT_K = 9; it is
+        # slower than the default now (75 us).
         x_variant = ATTN_XRES if (ctx.Lc <= 256 and ops.get_tuning(12) == ATTN_XRES) else 0
         for i, blk in enumerate(self.blocks):
             # ---- self-attention (model.py:283-289)

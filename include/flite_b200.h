@@ -55,6 +55,7 @@ extern "C" {
 #define FLITE_ATTN_2CTA_2WG_PTMEM 6
 #define FLITE_ATTN_QTMEM_1WG 7 /* cta_group::2, Q and P both TMEM operands, 64-key tiles, 6-stage K/V ring */
 #define FLITE_ATTN_QTMEM_2WG 8
+#define FLITE_ATTN_PERSISTENT 10  /* one wave of 2-CTA clusters, whole (sequence, head, 256-query tile) units round-robin, ragged lengths: variant 5's arithmetic without the per-unit launch cost (bit-identical to it) */
 #define FLITE_ATTN_XRES 9        /* persistent cross-attention, K/V (<= 256 keys per sequence, checked on the device) resident in the CTA pair */
 
 /* tuning knobs (A/B switches used by the benchmarks; defaults are the measured best) */

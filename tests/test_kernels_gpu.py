@@ -168,7 +168,7 @@ ATT_CASES = [(1, 1, 128, 128), (1, 2, 256, 384), (2, 2, 272, 272), (2, 2, 272, 1
              (2, 12, 4112, 256)]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 10])
 @pytest.mark.parametrize("B,H,Lq,Lk", ATT_CASES)
 def test_attention_uniform(B, H, Lq, Lk, variant):
     from flite_b200 import ops
@@ -184,7 +184,7 @@ def test_attention_uniform(B, H, Lq, Lk, variant):
     assert rel(out, ref.reshape(-1, d)) <= 5e-3          # bf16 output + bf16 P, same as FA2's own error
 
 
-@pytest.mark.parametrize("variant", [1, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("variant", [1, 3, 4, 5, 6, 7, 8, 10])
 def test_attention_ragged_and_empty_keys(variant):
     from flite_b200 import ops
     from oracle.dit_oracle import flash_attn_varlen
@@ -201,6 +201,29 @@ def test_attention_ragged_and_empty_keys(variant):
                             cu_q2, cu_k2, 256 ** -0.5)
     assert rel(out[ok], ref.reshape(-1, d)) <= 5e-3
     assert out[130:402].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("q_lens,k_lens,H", [([4112, 4112], [256, 256], 12), ([4112, 4112], [77, 256], 12),
+                                             ([300, 1, 272, 512, 4112], [129, 0, 272, 40, 1], 3),
+                                             ([1000] * 9, [256, 1, 0, 512, 300, 17, 128, 129, 255], 12)])
+def test_attention_persistent_ragged_bit_equal_to_per_unit_kernel(q_lens, k_lens, H):
+    """FLITE_ATTN_PERSISTENT (variant 10): one wave of clusters walks whole (sequence, head, 256-query tile) units
+    round-robin with per-sequence query / key lengths (the cross-attention over the packed text context,
+    model.py:188-210).  Same arithmetic per unit as variant 5, so the output must be bit-identical -- ragged query
+    tails, sequences shorter than a tile, an empty key sequence (zeros) and more units than clusters included -- and
+    nothing may be written outside the rows of the call."""
+    from flite_b200 import _lib, ops
+    cu_q = torch.tensor([0] + list(np.cumsum(q_lens)), dtype=torch.int32, device=DEV)
+    cu_k = torch.tensor([0] + list(np.cumsum(k_lens)), dtype=torch.int32, device=DEV)
+    nq, nk, d = sum(q_lens), sum(k_lens), H * 256
+    q, k, v = rnd(nq, d, seed=1), rnd(max(nk, 1), d, seed=2)[:nk], rnd(max(nk, 1), d, seed=3)[:nk]
+    base = ops.attention_varlen(q, k, v, cu_q, cu_k, H, max(q_lens), 1 / 16, variant=5)
+    out = torch.full((nq + 4, d), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.attention_varlen(q, k, v, cu_q, cu_k, H, max(q_lens), 1 / 16, variant=10, out=out[:nq])
+    again = ops.attention_varlen(q, k, v, cu_q, cu_k, H, max(q_lens), 1 / 16, variant=10)
+    _lib.watchdog_ok()
+    assert torch.equal(out[:nq], base) and torch.equal(again, base)
+    assert bool((out[nq:] == 7.0).all())
 
 
 def test_attention_self_from_qkv_buffer_full_size():

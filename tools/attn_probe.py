@@ -19,13 +19,14 @@ dev = "cuda"
 lib = _lib.load()
 _lib.check(lib.flite_check_device(), "flite_check_device")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-SHAPES = {"c2_self": (2, 12, 4112), "c4_self": (2, 12, 16400), "c4_sp4_rank": (2, 3, 16400), "c5_self": (8, 12, 4112),
+SHAPES = {"c2_cross": (2, 12, 4112, 256), "c3_cross": (16, 12, 4720, 256), "c2_self": (2, 12, 4112), "c4_self": (2, 12, 16400), "c4_sp4_rank": (2, 3, 16400), "c5_self": (8, 12, 4112),
           "c3_self": (16, 12, 4720)}
 # tag: (kind, variant, {tuning key: value})   kind "u" = one cluster per unit, "p" = persistent
 CASES = {
     "v5": ("u", 5, {}), "v6_2wg": ("u", 6, {}), 
     "v5_nosoftmax": ("u", 5, {3: 1}), "v5_noloads": ("u", 5, {3: 2}), "v5_neither": ("u", 5, {3: 3}),
     "v5_staged_stores": ("u", 5, {7: 1}), 
+    "v10_persistent": ("u", 10, {}), "v9_xres": ("u", 9, {}),
     "v5_rowstores": ("u", 5, {16: 1}), "v6_rowstores": ("u", 6, {16: 1}),
     "sk0_streamk": ("p", 0, {15: 0}), "sk1_roundrobin": ("p", 0, {15: 1}), "sk2_hybrid": ("p", 0, {15: 2}),
     "sk1_rr_noepilogue": ("p", 0, {15: 1, 3: 8}),
@@ -33,16 +34,18 @@ CASES = {
 names = args.cases.split(",") if args.cases else list(CASES)
 out = {}
 for shape in args.shapes.split(","):
-    B, H, L = SHAPES[shape]
+    B, H, L = SHAPES[shape][:3]
+    Lk = SHAPES[shape][3] if len(SHAPES[shape]) > 3 else L       # cross-attention shapes: Lk text keys per sequence
     g = torch.Generator(device=dev).manual_seed(0)
     d = H * 256
     qkv = torch.randn(B * L, 3 * d, device=dev, generator=g).bfloat16()
-    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    q, k, v = qkv[:, :d], qkv[:B * Lk, d:2 * d], qkv[:B * Lk, 2 * d:]
     cu = (torch.arange(B + 1, dtype=torch.int32) * L).to(dev)
+    cuk = (torch.arange(B + 1, dtype=torch.int32) * Lk).to(dev)
     scale = 256 ** -0.5
-    fl = 4.0 * B * H * L * L * 256
+    fl = 4.0 * B * H * L * Lk * 256
     ref = torch.empty(B * L, d, dtype=torch.bfloat16, device=dev)
-    ops.attention_varlen(q, k, v, cu, cu, H, L, scale, out=ref, variant=5)
+    ops.attention_varlen(q, k, v, cu, cuk, H, L, scale, out=ref, variant=5)
     o = torch.empty_like(ref)
 
     def run(tag):
@@ -50,9 +53,9 @@ for shape in args.shapes.split(","):
         for key, val in tune.items():
             lib.flite_set_tuning(key, val)
         if kind == "u":
-            ops.attention_varlen(q, k, v, cu, cu, H, L, scale, out=o, variant=variant)
+            ops.attention_varlen(q, k, v, cu, cuk, H, L, scale, out=o, variant=variant)
         else:
-            ops.attention_streamk(q, k, v, cu, cu, H, L, L, scale, out=o)
+            ops.attention_streamk(q, k, v, cu, cuk, H, L, Lk, scale, out=o)
         for key in tune:
             lib.flite_set_tuning(key, 0)
 
@@ -71,7 +74,7 @@ for shape in args.shapes.split(","):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); run(n); e1.record(); torch.cuda.synchronize()
             ts[n].append(e0.elapsed_time(e1))
-    nb = 40 if B * H * L * L < 2 * 12 * 10000 * 10000 else 6
+    nb = 40 if B * H * L * Lk < 2 * 12 * 10000 * 10000 else 6
     for rnd in range(2):
         for n in names:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
