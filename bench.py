@@ -547,8 +547,9 @@ def multi_gpu_layouts(model, dev, world, rank, steps):
             h = torch.tensor([rep.get("p2p signal+wait", (0, 0.0))[1]], device=dev, dtype=torch.float64)
             dist.all_reduce(h, op=dist.ReduceOp.MAX)
             hs = float(h.item())
-        # same layout with the stream-K self-attention where its heuristic picks it (model.attn_streamk = "auto": long
-        # sequences whose per-tile grid wastes >= 10 % of its last wave).  Not batch-invariant, hence a separate number.
+        # same layout with the hybrid self-attention schedule where its heuristic picks it (model.attn_streamk = "auto": long
+        # sequences whose whole-unit rounds waste >= 10 % of the last one; whole rounds in lock step + stream-K shares over
+        # the rest).  Not batch-invariant, hence a separate number.
         sk = None
         if sp_group is not None and model._use_streamk_auto(1 if cfg_group is not None else 2,
                                                             arch["num_heads"] // sp_ranks, 16 + (height // 16) * (width // 16)):
@@ -560,7 +561,8 @@ def multi_gpu_layouts(model, dev, world, rank, steps):
             dist.all_reduce(r_sk, op=dist.ReduceOp.MAX)
             ms_sk = timed(step, n)
             model.attn_streamk = sk_default
-            sk = {"ms_per_step": ms_sk, "speedup_vs_1gpu": ms1 / ms_sk, "rel_l2_vs_1gpu": float(r_sk.item())}
+            sk = {"schedule": "hybrid: whole rounds in lock step + stream-K shares over the last 1..2 units per cluster",
+                  "ms_per_step": ms_sk, "speedup_vs_1gpu": ms1 / ms_sk, "rel_l2_vs_1gpu": float(r_sk.item())}
         _lib.watchdog_ok()
         model.enable_sequence_parallel(None)
         name = "x".join(p for p in ((f"cfg{cfg_ranks}" if cfg_ranks > 1 else ""), (f"sp{sp_ranks}" if sp_ranks > 1 else "")) if p)

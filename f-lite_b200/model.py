@@ -192,12 +192,13 @@ class DiT(nn.Module):
         #   "0"             flite_attention_varlen with FLITE_ATTN_AUTO: the same persistent kernel in its ragged-length
         #                   mode (what the cross-attention calls use); FLITE_TUNE_ATTN_VARIANT = 5 selects the round-1 path,
         #                   one cluster per unit.
-        #   "1" / "auto"    stream-K shares: a unit split between two clusters is merged in fp32, so the result depends on
+        #   "1"             stream-K shares: a unit split between two clusters is merged in fp32, so the result depends on
         #                   where the shares fall (batch size / head count); loses 8 % at C2 (the clusters no longer walk the
-        #                   same key tiles in lock step: 1.0 GB of DRAM reads per launch instead of 0.15), wins on a
-        #                   sequence-parallel rank's 3 heads x 16400 tokens.  "auto" picks it when the per-unit grid wastes
-        #                   >= 10 % of its last wave on long sequences.
-        #   "hybrid"        whole rounds in lock step, stream-K shares over the last 1..2 units per cluster.
+        #                   same key tiles in lock step: 1.0 GB of DRAM reads per launch instead of 0.15).
+        #   "hybrid"        whole rounds in lock step, stream-K shares over the last 1..2 units per cluster: same caveat
+        #                   (not batch-invariant), but it removes the last-round quantisation without the L2 cost:
+        #                   -6 % on a sequence-parallel rank's 2 x 3 heads x 16400 tokens (5.27 -> 6 rounds), -3 % at C4.
+        #   "auto"          "hybrid" for long sequences whose last round is >= 10 % empty, else "rr".
         self.attn_streamk = os.environ.get("FLITE_ATTN_STREAMK", "rr")
         self.gemm_variant = GEMM_AUTO
         self.sp_group = None      # Ulysses sequence-parallel process group (see enable_sequence_parallel)
@@ -248,16 +249,16 @@ class DiT(nn.Module):
         return self._sp_sym[1:]
 
     def _use_streamk(self, B, heads, L):
+        """Picks the schedule of the persistent self-attention kernel (FLITE_TUNE_ATTN_SK_MODE) for this call; False =
+        go through flite_attention_varlen (FLITE_ATTN_AUTO) instead."""
         mode = self.attn_streamk
-        if mode in ("rr", "hybrid"):
-            _lib.load().flite_set_tuning(15, 1 if mode == "rr" else 2)
-            return True
-        _lib.load().flite_set_tuning(15, 0)
-        if mode in (True, "1", 1):
-            return True
-        if mode != "auto":
+        if mode == "auto":   # long sequences whose whole-unit rounds waste >= 10 % of the last one: hybrid, else round-robin
+            mode = "hybrid" if self._use_streamk_auto(B, heads, L) else "rr"
+        sk = {"rr": 1, "hybrid": 2, "1": 0, 1: 0, True: 0}.get(mode)
+        if sk is None:
             return False
-        return self._use_streamk_auto(B, heads, L)
+        _lib.load().flite_set_tuning(15, sk)
+        return True
 
     def _use_streamk_auto(self, B, heads, L):
         units = B * heads * ((L + 255) // 256)

@@ -19,7 +19,7 @@ dev = "cuda"
 lib = _lib.load()
 _lib.check(lib.flite_check_device(), "flite_check_device")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-SHAPES = {"c2_cross": (2, 12, 4112, 256), "c3_cross": (16, 12, 4720, 256), "c2_self": (2, 12, 4112), "c4_self": (2, 12, 16400), "c4_sp4_rank": (2, 3, 16400), "c5_self": (8, 12, 4112),
+SHAPES = {"c2_cross": (2, 12, 4112, 256), "c3_cross": (16, 12, 4720, 256), "c2_self": (2, 12, 4112), "c4_self": (2, 12, 16400), "c4_sp4_rank": (2, 3, 16400), "c4_cfg2sp4_rank": (1, 3, 16400), "c4_sp2_rank": (2, 6, 16400), "c5_self": (8, 12, 4112),
           "c3_self": (16, 12, 4720)}
 # tag: (kind, variant, {tuning key: value})   kind "u" = one cluster per unit, "p" = persistent
 CASES = {
