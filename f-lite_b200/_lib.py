@@ -30,6 +30,8 @@ SIGNATURES = {
     "flite_apg_euler": [_P, _I, _P, _P, _F, _F, _F, _P, _L, _P, _P],
     "flite_latent_unscale": [_P, _P, _F, _F, _L, _P],
     "flite_image_to_uint8": [_P, _I, _P, _I, _I, _I, _I, _P],
+    "flite_groupnorm_partials_bytes": [_I, _I, _I],
+    "flite_groupnorm_silu_nhwc": [_P, _P, _P, _P, _I, _L, _I, _I, _F, _I, _P, _I, _P],
     "flite_rmsnorm_modulate": [_P, _L, _P, _L, _P, _I, _P, _P, _L, _I, _I, _I, _F, _P],
     "flite_rope_qknorm": [_P, _L, _I, _I, _P, _P, _I, _F, _P],
     "flite_patch_embed": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -81,7 +83,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = (c_char_p if name == "flite_last_error"
-                      else c_int64 if name == "flite_attention_streamk_workspace_bytes" else c_int)
+                      else c_int64 if name in ("flite_attention_streamk_workspace_bytes", "flite_groupnorm_partials_bytes")
+                      else c_int)
     _lib = lib
     return lib
 

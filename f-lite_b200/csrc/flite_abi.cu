@@ -18,6 +18,7 @@
 #include "attn_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
+#include "groupnorm.cuh"
 
 using namespace flite;
 
@@ -331,6 +332,35 @@ int flite_latent_unscale(const void* latents, void* out, float scaling_factor, f
     if (blocks > cap) blocks = cap;
     latent_unscale_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)latents, (__nv_bfloat16*)out,
                                                                     1.0f / scaling_factor, shift_factor, n8);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t flite_groupnorm_partials_bytes(int N, int groups, int splits) {
+    return (int64_t)N * groups * splits * (int64_t)sizeof(float2);
+}
+
+int flite_groupnorm_silu_nhwc(const void* x, void* y, const void* gamma, const void* beta, int N, int64_t HW, int C,
+                              int groups, float eps, int apply_silu, void* partials, int splits, void* stream) {
+    if (!x || !y || !gamma || !beta || !partials) return fail(FLITE_ERR_INVALID, "groupnorm: null pointer");
+    if (N <= 0 || HW <= 0) return 0;
+    if (C % 8 || groups <= 0 || groups > 64 || C % groups || (C / groups) % 4 || C / 8 > GN_THREADS || splits <= 0)
+        return fail(FLITE_ERR_INVALID, "groupnorm: needs C %% 8 == 0, (C / groups) %% 4 == 0, groups <= 64, C <= 2048 (C %d, groups %d)",
+                    C, groups);
+    if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15)
+        return fail(FLITE_ERR_INVALID, "groupnorm: pointers must be 16-byte aligned");
+    const int chunks = C / 8, lanes = GN_THREADS / chunks;
+    const size_t smem = (size_t)lanes * chunks * 16;
+    groupnorm_stats_kernel<<<dim3(splits, N), GN_THREADS, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (long long)HW, C, groups, (float2*)partials);
+    LAUNCH_CHECK();
+    long long blocks = (HW * chunks + GN_THREADS * 4 - 1) / (GN_THREADS * 4);
+    const long long cap = (long long)num_sms() * 8 / (N > 0 ? 1 : 1);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    groupnorm_apply_kernel<<<dim3((unsigned)blocks, N), GN_THREADS, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (long long)HW, C,
+        groups, eps, apply_silu, (const float2*)partials, splits);
     LAUNCH_CHECK();
     return 0;
 }

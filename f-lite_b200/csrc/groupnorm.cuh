@@ -1,0 +1,103 @@
+// GroupNorm (+ SiLU) for channels-last activations: the VAE decoder's norm -> activation pairs
+// (diffusers ResnetBlock2D / Attention.group_norm / conv_norm_out behind f_lite/pipeline.py:299-307).  HBM-bound:
+// x [N, HW, C] bf16 is read twice (statistics, apply) and written once; torch runs the same thing as a row-moments kernel
+// plus unvectorised elementwise kernels on the channels-last tensor (85 % of the decode time at 1024^2, tools/vae_probe.py).
+//   pass 1  groupnorm_stats_kernel : per (image, pixel slice) partial sum / sum of squares of every group, fixed order
+//   pass 2  groupnorm_apply_kernel : mean / rstd from the partials (double, fixed order), y = bf16(x*a + b) [, silu -> bf16]
+// Deterministic (no atomics).  Rounding points as in torch's bf16 path (aten group_norm_kernel.cu, what diffusers' VAE runs
+// in bf16): mean and rstd are STORED in the activation dtype (bf16) before use, the affine is folded as a = rstd * gamma,
+// b = beta - a * mean in fp32, y = bf16(a * x + b); SiLU is evaluated in fp32 on that bf16 value and rounded again.
+#pragma once
+
+#include "common.cuh"
+
+namespace flite {
+
+constexpr int GN_THREADS = 256;
+
+// grid (splits, N).  Requires C % 8 == 0, (C / groups) % 4 == 0, C / 8 <= GN_THREADS, groups <= 64.
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, long long hw, int C, int groups, float2* __restrict__ partials) {
+    extern __shared__ float gn_smem[];                       // [pixel lanes][C / 4 halves][2]
+    const int n = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+    const int chunks = C >> 3;                               // 16-byte chunks per pixel
+    const int lanes = GN_THREADS / chunks;                   // pixels processed per iteration
+    const int c = threadIdx.x % chunks, pl = threadIdx.x / chunks;
+    const long long p0 = hw * split / splits, p1 = hw * (split + 1) / splits;
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;            // channels [8c, 8c+4) and [8c+4, 8c+8)
+    if (pl < lanes) {
+        const uint4* base = reinterpret_cast<const uint4*>(x + ((long long)n * hw) * C) + c;
+        for (long long p = p0 + pl; p < p1; p += lanes) {
+            const uint4 v = __ldcg(base + p * chunks);
+            const float a0 = bf16_lo(v.x), a1 = bf16_hi(v.x), a2 = bf16_lo(v.y), a3 = bf16_hi(v.y);
+            const float b0 = bf16_lo(v.z), b1 = bf16_hi(v.z), b2 = bf16_lo(v.w), b3 = bf16_hi(v.w);
+            s0 += (a0 + a1) + (a2 + a3);
+            q0 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+            s1 += (b0 + b1) + (b2 + b3);
+            q1 += (b0 * b0 + b1 * b1) + (b2 * b2 + b3 * b3);
+        }
+        float* slot = gn_smem + ((size_t)pl * (2 * chunks) + 2 * c) * 2;
+        slot[0] = s0; slot[1] = q0; slot[2] = s1; slot[3] = q1;
+    }
+    __syncthreads();
+    // one thread per group: its halves (4 channels each) over all pixel lanes, fixed order
+    if (threadIdx.x < groups) {
+        const int halves_per_group = (C / groups) >> 2;
+        float s = 0.f, q = 0.f;
+        for (int l = 0; l < lanes; ++l)
+            for (int hh = 0; hh < halves_per_group; ++hh) {
+                const float* slot = gn_smem + ((size_t)l * (2 * chunks) + threadIdx.x * halves_per_group + hh) * 2;
+                s += slot[0]; q += slot[1];
+            }
+        partials[((long long)n * splits + split) * groups + threadIdx.x] = make_float2(s, q);
+    }
+}
+
+// grid (blocks, N)
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                       const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, long long hw, int C,
+                       int groups, float eps, int apply_silu, const float2* __restrict__ partials, int splits) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int n = blockIdx.y;
+    if (threadIdx.x < groups) {
+        double s = 0.0, q = 0.0;
+        for (int i = 0; i < splits; ++i) {
+            const float2 v = partials[((long long)n * splits + i) * groups + threadIdx.x];
+            s += (double)v.x; q += (double)v.y;
+        }
+        const double cnt = (double)hw * (double)(C / groups);
+        const double mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = bf16_round((float)mean);                       // torch keeps mean / rstd in the input dtype
+        s_rstd[threadIdx.x] = bf16_round(rsqrtf((float)var + eps));
+    }
+    __syncthreads();
+    const int chunks = C >> 3, cpg = C / groups;
+    const long long total = hw * chunks;
+    const uint4* xin = reinterpret_cast<const uint4*>(x + ((long long)n * hw) * C);
+    uint4* yout = reinterpret_cast<uint4*>(y + ((long long)n * hw) * C);
+    for (long long i = (long long)blockIdx.x * GN_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * GN_THREADS) {
+        const int c = (int)(i % chunks);
+        const uint4 v = __ldcg(xin + i);
+        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma) + c);
+        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta) + c);
+        const int g0 = (8 * c) / cpg, g1 = (8 * c + 4) / cpg;
+        const float m0 = s_mean[g0], r0 = s_rstd[g0], m1 = s_mean[g1], r1 = s_rstd[g1];
+        const uint32_t xw[4] = {v.x, v.y, v.z, v.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float m = j < 2 ? m0 : m1, r = j < 2 ? r0 : r1;
+            const float ca = r * bf16_lo(gw[j]), cb = r * bf16_hi(gw[j]);          // a = rstd * gamma
+            float a = bf16_round(fmaf(bf16_lo(xw[j]), ca, bf16_lo(bw[j]) - ca * m));   // y = a * x + (beta - a * mean)
+            float b = bf16_round(fmaf(bf16_hi(xw[j]), cb, bf16_hi(bw[j]) - cb * m));
+            if (apply_silu) { a = silu_f(a); b = silu_f(b); }
+            o[j] = pack_bf16x2(a, b);
+        }
+        yout[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+}  // namespace flite

@@ -165,6 +165,38 @@ def image_to_uint8(decoded: torch.Tensor, out: Optional[torch.Tensor] = None) ->
     return out
 
 
+_GN_WS = {}
+
+
+def groupnorm_silu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, groups: int, eps: float = 1e-6,
+                   silu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm (+ SiLU) of a channels-last [N, C, H, W] bf16 activation in two launches (flite_groupnorm_silu_nhwc):
+    the VAE decoder's norm -> nonlinearity pairs (diffusers ResnetBlock2D / conv_norm_out, f_lite/pipeline.py:299-307)."""
+    lib = _lib.load()
+    if not (x.is_cuda and x.dtype == BF16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)):
+        raise _lib.FliteError("groupnorm_silu: expected a channels-last CUDA bf16 [N, C, H, W] tensor")
+    N, C, H, W = x.shape
+    if out is None:
+        out = torch.empty_like(x)           # keeps the channels-last strides
+    elif out.shape != x.shape or out.stride() != x.stride() or out.dtype != BF16:
+        raise _lib.FliteError("groupnorm_silu: out must match x (shape, channels-last strides, bf16)")
+    w = weight if weight.dtype == BF16 else weight.to(BF16)
+    b = bias if bias.dtype == BF16 else bias.to(BF16)
+    splits = max(1, min(64, (2 * torch.cuda.get_device_properties(x.device).multi_processor_count + N - 1) // N,
+                        (H * W + 255) // 256))
+    key = (x.device, N, groups, splits)
+    ws = _GN_WS.get(key)
+    if ws is None:
+        _GN_WS.clear()
+        ws = _GN_WS[key] = torch.empty(int(lib.flite_groupnorm_partials_bytes(N, groups, splits)) // 4, dtype=torch.float32,
+                                       device=x.device)
+    _lib.check(lib.flite_groupnorm_silu_nhwc(x.data_ptr(), out.data_ptr(), w.contiguous().data_ptr(), b.contiguous().data_ptr(),
+                                             N, H * W, C, groups, float(eps), int(silu), ws.data_ptr(), splits, _stream()),
+               "groupnorm_silu")
+    LAUNCHES[0] += 2
+    return out
+
+
 @_traced(lambda x, *a, **k: f"rmsnorm_modulate {tuple(x.shape)}")
 def rmsnorm_modulate(x: torch.Tensor, weight: Optional[torch.Tensor], weight_mode: int,
                      scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,

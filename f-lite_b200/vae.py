@@ -9,9 +9,13 @@ decoder is provided by this module with **diffusers' parameter names** (``decode
 (names restated from diffusers' ``models/autoencoders/vae.py``; encoder / quant-conv keys are ignored with
 ``strict=False``).
 
-This is **not** part of the denoise hot path: convolutions, group norms and the single mid-block attention run on
-cuDNN / cuBLAS / SDPA through torch (library code, 0.05 % of a 30-step image's FLOPs); what is hand-written around it
-is the pipeline tail -- ``flite_latent_unscale`` before and ``flite_image_to_uint8`` after (``ops.py``).
+This is **not** part of the denoise hot path.  Profiled at 1024^2 (``tools/vae_probe.py``): the convolutions are the
+cheap part of a decode (cuDNN's sm_100 implicit-GEMM kernels, ~1080 TFLOP/s, 10 % of the time) -- 85 % went to torch's
+GroupNorm row-moments kernel and unvectorised elementwise kernels on the channels-last activations.  On a CUDA bf16
+channels-last tensor the norm -> SiLU pairs therefore run as ``flite_groupnorm_silu_nhwc`` (``csrc/groupnorm.cuh``, two
+HBM-bound launches); convolutions and the single mid-block attention stay on cuDNN / SDPA through torch (library code);
+on the CPU (``tests/test_vae_cpu.py``, the oracle comparison) everything is torch.  Around the decoder the pipeline tail
+is ``flite_latent_unscale`` before and ``flite_image_to_uint8`` after (``ops.py``).
 """
 from __future__ import annotations
 
@@ -20,6 +24,16 @@ from types import SimpleNamespace
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+
+def _gn(x: torch.Tensor, norm: nn.GroupNorm, silu: bool) -> torch.Tensor:
+    """GroupNorm (+ SiLU): the sm_100a kernel pair for channels-last CUDA bf16 activations, torch otherwise."""
+    if (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+            and x.shape[1] % 8 == 0 and (x.shape[1] // norm.num_groups) % 4 == 0 and norm.num_groups <= 64):
+        from . import ops
+        return ops.groupnorm_silu(x, norm.weight, norm.bias, norm.num_groups, norm.eps, silu=silu)
+    y = norm(x)
+    return F.silu(y) if silu else y
 
 
 class ResnetBlock2D(nn.Module):
@@ -32,8 +46,8 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x):
-        h = self.conv1(F.silu(self.norm1(x)))
-        h = self.conv2(F.silu(self.norm2(h)))
+        h = self.conv1(_gn(x, self.norm1, True))
+        h = self.conv2(_gn(h, self.norm2, True))
         return (x if self.conv_shortcut is None else self.conv_shortcut(x)) + h
 
 
@@ -48,7 +62,7 @@ class Attention(nn.Module):
 
     def forward(self, x):
         b, c, h, w = x.shape
-        t = self.group_norm(x).flatten(2).transpose(1, 2)
+        t = _gn(x, self.group_norm, False).flatten(2).transpose(1, 2)
         a = F.scaled_dot_product_attention(self.to_q(t)[:, None], self.to_k(t)[:, None], self.to_v(t)[:, None])[:, 0]
         return x + self.to_out[0](a).transpose(1, 2).reshape(b, c, h, w)
 
@@ -104,7 +118,7 @@ class Decoder(nn.Module):
         h = self.mid_block(self.conv_in(z))
         for blk in self.up_blocks:
             h = blk(h)
-        return self.conv_out(F.silu(self.conv_norm_out(h)))
+        return self.conv_out(_gn(h, self.conv_norm_out, True))
 
 
 class AutoencoderKL(nn.Module):

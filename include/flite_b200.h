@@ -113,6 +113,16 @@ int flite_latent_unscale(const void* latents, void* out, float scaling_factor, f
                          void* stream);
 int flite_image_to_uint8(const void* decoded, int in_is_fp32, void* out_u8, int B, int C, int H, int W, void* stream);
 
+/* GroupNorm (+ SiLU) on channels-last activations x[N, HW, C] (bf16): the norm -> activation pairs of the VAE decoder the
+ * pipeline decodes with (diffusers AutoencoderKL.decode behind f_lite/pipeline.py:299-307: ResnetBlock2D.norm1/norm2 +
+ * nonlinearity, Attention.group_norm, Decoder.conv_norm_out + conv_act).  Two launches (per-slice partial sums in a fixed
+ * order, then normalise): deterministic, statistics in fp32 / double, GroupNorm output rounded to bf16 before the SiLU like
+ * the torch op pair.  `partials` is caller-owned scratch of flite_groupnorm_partials_bytes(N, groups, splits) bytes.
+ * Requires C % 8 == 0, (C / groups) % 4 == 0, groups <= 64, C <= 2048, 16-byte aligned pointers. */
+int64_t flite_groupnorm_partials_bytes(int N, int groups, int splits);
+int flite_groupnorm_silu_nhwc(const void* x, void* y, const void* gamma, const void* beta, int N, int64_t HW, int C,
+                              int groups, float eps, int apply_silu, void* partials, int splits, void* stream);
+
 /* y = RMSNorm(x)[*w] [*(1+scale[s]) + shift[s]], s = row / rows_per_sample.   model.py:238,283-284,292-293,299-300,437,579-580
  *   weight_mode 0 none | 1 Liger "llama" casting | 2 reference RMSNorm (fp32 weight multiply)
  *   scale/shift may be NULL (no modulation); they index a [B, ld_mod] modulation matrix */

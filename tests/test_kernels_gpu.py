@@ -756,3 +756,32 @@ def test_attention_streamk_rejects_ragged_lengths():
     ops.attention_streamk(q, k, v, cu, cu, H, 300, 300, 256 ** -0.5)
     with pytest.raises(_lib.FliteError):
         _lib.watchdog_ok()
+
+
+# ----------------------------------------------------------------------------- VAE decoder norm (next row: pipeline tail)
+@pytest.mark.parametrize("N,C,H,W,silu", [(2, 128, 64, 64, True), (1, 256, 32, 48, True), (3, 512, 16, 16, True),
+                                          (1, 512, 24, 24, False), (1, 128, 1024, 1024, True)])
+def test_groupnorm_silu_nhwc_vs_torch(N, C, H, W, silu):
+    """flite_groupnorm_silu_nhwc (the VAE decoder's GroupNorm -> SiLU pairs, diffusers ResnetBlock2D behind
+    f_lite/pipeline.py:299-307) against torch's group_norm (+ silu) on the same channels-last bf16 tensor -- the kernel
+    reproduces torch's bf16 rounding points (mean / rstd stored in bf16, folded affine in fp32, norm output rounded to
+    bf16 before the activation), so all but a few near-tie elements are bit-equal -- and against the fp32 op on the same
+    input (bounded by the bf16 rstd: 2^-9).  Deterministic: a second launch reproduces the first."""
+    import torch.nn.functional as F
+    from flite_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(N * 1000 + C)
+    x = (torch.randn(N, C, H, W, device=DEV, generator=g) * 1.7 + 0.3).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(C, device=DEV, generator=g) * 0.5 + 1.0).bfloat16()
+    b = (torch.randn(C, device=DEV, generator=g) * 0.2).bfloat16()
+    got = ops.groupnorm_silu(x, w, b, 32, 1e-6, silu=silu)
+    again = ops.groupnorm_silu(x, w, b, 32, 1e-6, silu=silu)
+    assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, again)
+    ref = F.group_norm(x, 32, w, b, 1e-6)
+    ref32 = F.group_norm(x.float(), 32, w.float(), b.float(), 1e-6)
+    if silu:
+        ref, ref32 = F.silu(ref), F.silu(ref32)
+    assert rel(got, ref32) <= 6e-3                       # bf16 rstd / mean + bf16 outputs, same as torch's own bf16 path
+    assert rel(ref, ref32) <= 6e-3
+    differ = (got != ref).float().mean().item()
+    print(f"groupnorm vs torch bf16: {differ:.2e} of the elements differ, rel {rel(got, ref):.2e}")
+    assert differ <= 1e-4 and rel(got, ref) <= 1e-4       # measured: bit-equal on every case
