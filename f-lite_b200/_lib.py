@@ -31,6 +31,8 @@ SIGNATURES = {
     "flite_latent_unscale": [_P, _P, _F, _F, _L, _P],
     "flite_image_to_uint8": [_P, _I, _P, _I, _I, _I, _I, _P],
     "flite_groupnorm_partials_bytes": [_I, _I, _I],
+    "flite_bias_residual_add_nhwc": [_P, _P, _P, _L, _I, _P],
+    "flite_upsample_nearest2x_nhwc": [_P, _P, _I, _I, _I, _I, _P],
     "flite_groupnorm_silu_nhwc": [_P, _P, _P, _P, _I, _L, _I, _I, _F, _I, _P, _I, _P],
     "flite_rmsnorm_modulate": [_P, _L, _P, _L, _P, _I, _P, _P, _L, _I, _I, _I, _F, _P],
     "flite_rope_qknorm": [_P, _L, _I, _I, _P, _P, _I, _F, _P],

@@ -365,6 +365,34 @@ int flite_groupnorm_silu_nhwc(const void* x, void* y, const void* gamma, const v
     return 0;
 }
 
+int flite_upsample_nearest2x_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+    if (!x || !y) return fail(FLITE_ERR_INVALID, "upsample: null pointer");
+    if (N <= 0 || H <= 0 || W <= 0) return 0;
+    if (C % 8 || (((uintptr_t)x | (uintptr_t)y) & 15))
+        return fail(FLITE_ERR_INVALID, "upsample: C must be a multiple of 8 and the pointers 16-byte aligned");
+    long long blocks = ((long long)N * H * W * (C / 8) + 256 * 2 - 1) / (256 * 2);
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    upsample_nearest2x_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x,
+                                                                                       (__nv_bfloat16*)y, N, H, W, C);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int flite_bias_residual_add_nhwc(void* y, const void* bias, const void* residual, int64_t rows, int C, void* stream) {
+    if (!y || !bias) return fail(FLITE_ERR_INVALID, "bias_residual_add: null pointer");
+    if (rows <= 0) return 0;
+    if (C % 8 || (((uintptr_t)y | (uintptr_t)bias | (uintptr_t)residual) & 15))
+        return fail(FLITE_ERR_INVALID, "bias_residual_add: C must be a multiple of 8 and the pointers 16-byte aligned");
+    long long blocks = (rows * (C / 8) + 256 * 4 - 1) / (256 * 4);
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    bias_residual_add_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)y, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, (long long)rows, C);
+    LAUNCH_CHECK();
+    return 0;
+}
+
 int flite_image_to_uint8(const void* decoded, int in_is_fp32, void* out_u8, int B, int C, int H, int W, void* stream) {
     if (!decoded || !out_u8) return fail(FLITE_ERR_INVALID, "image_to_uint8: null pointer");
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;

@@ -182,7 +182,7 @@ def groupnorm_silu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, gr
         raise _lib.FliteError("groupnorm_silu: out must match x (shape, channels-last strides, bf16)")
     w = weight if weight.dtype == BF16 else weight.to(BF16)
     b = bias if bias.dtype == BF16 else bias.to(BF16)
-    splits = max(1, min(64, (2 * torch.cuda.get_device_properties(x.device).multi_processor_count + N - 1) // N,
+    splits = max(1, min(512, (8 * torch.cuda.get_device_properties(x.device).multi_processor_count + N - 1) // N,
                         (H * W + 255) // 256))
     key = (x.device, N, groups, splits)
     ws = _GN_WS.get(key)
@@ -195,6 +195,35 @@ def groupnorm_silu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, gr
                "groupnorm_silu")
     LAUNCHES[0] += 2
     return out
+
+
+def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
+    """Nearest-neighbour 2x upsampling of a channels-last [N, C, H, W] bf16 activation (diffusers Upsample2D)."""
+    lib = _lib.load()
+    if not (x.is_cuda and x.dtype == BF16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)):
+        raise _lib.FliteError("upsample_nearest2x: expected a channels-last CUDA bf16 [N, C, H, W] tensor")
+    N, C, H, W = x.shape
+    out = torch.empty((N, C, 2 * H, 2 * W), dtype=BF16, device=x.device, memory_format=torch.channels_last)
+    _lib.check(lib.flite_upsample_nearest2x_nhwc(x.data_ptr(), out.data_ptr(), N, H, W, C, _stream()), "upsample_nearest2x")
+    LAUNCHES[0] += 1
+    return out
+
+
+def bias_residual_add_(y: torch.Tensor, bias: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In place on a channels-last [N, C, H, W] bf16 conv output: y = bf16(y + bias); y = bf16(residual + y) if given."""
+    lib = _lib.load()
+    cl = torch.channels_last
+    if not (y.is_cuda and y.dtype == BF16 and y.dim() == 4 and y.is_contiguous(memory_format=cl)):
+        raise _lib.FliteError("bias_residual_add_: expected a channels-last CUDA bf16 [N, C, H, W] tensor")
+    if residual is not None and not (residual.shape == y.shape and residual.dtype == BF16
+                                     and residual.is_contiguous(memory_format=cl)):
+        raise _lib.FliteError("bias_residual_add_: residual must match y (shape, channels-last, bf16)")
+    N, C, H, W = y.shape
+    b = bias if bias.dtype == BF16 else bias.to(BF16)
+    _lib.check(lib.flite_bias_residual_add_nhwc(y.data_ptr(), b.contiguous().data_ptr(), _ptr(residual), N * H * W, C,
+                                                _stream()), "bias_residual_add")
+    LAUNCHES[0] += 1
+    return y
 
 
 @_traced(lambda x, *a, **k: f"rmsnorm_modulate {tuple(x.shape)}")

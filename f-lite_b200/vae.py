@@ -26,14 +26,39 @@ import torch.nn.functional as F
 from torch import nn
 
 
+# False = run the norm / bias / skip-connection passes through torch as well (A/B and parity tests)
+USE_NATIVE_KERNELS = True
+
+
 def _gn(x: torch.Tensor, norm: nn.GroupNorm, silu: bool) -> torch.Tensor:
     """GroupNorm (+ SiLU): the sm_100a kernel pair for channels-last CUDA bf16 activations, torch otherwise."""
-    if (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
-            and x.shape[1] % 8 == 0 and (x.shape[1] // norm.num_groups) % 4 == 0 and norm.num_groups <= 64):
+    if (USE_NATIVE_KERNELS and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
+            and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 8 == 0 and (x.shape[1] // norm.num_groups) % 4 == 0 and norm.num_groups <= 64):
         from . import ops
         return ops.groupnorm_silu(x, norm.weight, norm.bias, norm.num_groups, norm.eps, silu=silu)
     y = norm(x)
     return F.silu(y) if silu else y
+
+
+def _native(x: torch.Tensor, channels: int) -> bool:
+    return (USE_NATIVE_KERNELS and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and channels % 8 == 0
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def _conv(x: torch.Tensor, conv: nn.Conv2d, residual: torch.Tensor | None = None) -> torch.Tensor:
+    """conv(x) [+ residual].  On the CUDA bf16 channels-last path the convolution itself is cuDNN's (library code, run
+    without its bias) and the bias + skip connection are one vectorised in-place pass (flite_bias_residual_add_nhwc)
+    with torch's rounding points; anywhere else plain torch."""
+    if conv.bias is not None and _native(x, conv.out_channels):
+        y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
+        if y.is_contiguous(memory_format=torch.channels_last) and (
+                residual is None or (residual.shape == y.shape and residual.is_contiguous(memory_format=torch.channels_last))):
+            from . import ops
+            return ops.bias_residual_add_(y, conv.bias, residual)
+        y = y + conv.bias.view(1, -1, 1, 1)
+        return y if residual is None else residual + y
+    y = conv(x)
+    return y if residual is None else residual + y
 
 
 class ResnetBlock2D(nn.Module):
@@ -46,9 +71,9 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x):
-        h = self.conv1(_gn(x, self.norm1, True))
-        h = self.conv2(_gn(h, self.norm2, True))
-        return (x if self.conv_shortcut is None else self.conv_shortcut(x)) + h
+        h = _conv(_gn(x, self.norm1, True), self.conv1)
+        skip = x if self.conv_shortcut is None else _conv(x, self.conv_shortcut)
+        return _conv(_gn(h, self.norm2, True), self.conv2, residual=skip)
 
 
 class Attention(nn.Module):
@@ -83,7 +108,10 @@ class _Upsample(nn.Module):
         self.conv = nn.Conv2d(c, c, 3, padding=1)
 
     def forward(self, x):
-        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+        if _native(x, x.shape[1]):
+            from . import ops
+            return _conv(ops.upsample_nearest2x(x), self.conv)
+        return _conv(F.interpolate(x, scale_factor=2.0, mode="nearest"), self.conv)
 
 
 class _UpBlock(nn.Module):
@@ -115,7 +143,7 @@ class Decoder(nn.Module):
         self.conv_out = nn.Conv2d(ch[-1], out_channels, 3, padding=1)
 
     def forward(self, z):
-        h = self.mid_block(self.conv_in(z))
+        h = self.mid_block(_conv(z, self.conv_in))
         for blk in self.up_blocks:
             h = blk(h)
         return self.conv_out(_gn(h, self.conv_norm_out, True))

@@ -120,6 +120,13 @@ int flite_image_to_uint8(const void* decoded, int in_is_fp32, void* out_u8, int 
  * the torch op pair.  `partials` is caller-owned scratch of flite_groupnorm_partials_bytes(N, groups, splits) bytes.
  * Requires C % 8 == 0, (C / groups) % 4 == 0, groups <= 64, C <= 2048, 16-byte aligned pointers. */
 int64_t flite_groupnorm_partials_bytes(int N, int groups, int splits);
+/* y[rows, C] (channels-last conv output, bf16) = bf16(y + bias[C]); if residual != NULL then y = bf16(residual + y): the
+ * bias of the decoder's convolutions (torch applies it as a separate broadcast add_ on the cuDNN output) and the
+ * ResnetBlock2D skip connection (diffusers resnet.py: output = input + hidden) in one in-place pass. */
+int flite_bias_residual_add_nhwc(void* y, const void* bias, const void* residual, int64_t rows, int C, void* stream);
+/* y[N, 2H, 2W, C] = nearest-neighbour 2x upsampling of the channels-last x[N, H, W, C] (bf16; diffusers Upsample2D:
+ * F.interpolate(scale_factor=2.0, mode="nearest") before its convolution).  C % 8 == 0. */
+int flite_upsample_nearest2x_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);
 int flite_groupnorm_silu_nhwc(const void* x, void* y, const void* gamma, const void* beta, int N, int64_t HW, int C,
                               int groups, float eps, int apply_silu, void* partials, int splits, void* stream);
 

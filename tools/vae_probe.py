@@ -1,9 +1,12 @@
-import sys, time, torch
-sys.path.insert(0, "/root/repo")
+"""Where a VAE decode goes (4 images, 1024^2, bf16 channels-last): per-kernel CUDA time of flite_b200.vae.AutoencoderKL.decode
+(torch profiler), with the native GroupNorm+SiLU path and, for comparison, torch's own (FLITE_VAE_TORCH_NORM=1)."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from flite_b200 import vae as V
+from torch.profiler import profile, ProfilerActivity
 dev = "cuda"
 torch.manual_seed(0)
-m = V.AutoencoderKL().to(dev, torch.bfloat16).eval()
+m = V.AutoencoderKL().to(dev, torch.bfloat16).to(memory_format=torch.channels_last).eval()
 z = torch.randn(4, 16, 128, 128, device=dev, dtype=torch.bfloat16)
 def timeit(fn, n=3):
     fn(); torch.cuda.synchronize()
@@ -13,18 +16,8 @@ def timeit(fn, n=3):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 with torch.no_grad():
-    ref = m.decode(z).sample.float()
-    print("baseline ms", timeit(lambda: m.decode(z)))
-    m.enable_slicing(); print("slicing ms", timeit(lambda: m.decode(z))); m.disable_slicing()
-    torch.backends.cudnn.benchmark = True
-    print("cudnn.benchmark ms", timeit(lambda: m.decode(z)))
-    m.decoder.to(memory_format=torch.channels_last)
-    out = m.decode(z).sample.float()
-    print("channels_last weights ms", timeit(lambda: m.decode(z)), "rel", ((out - ref).norm() / ref.norm()).item())
-    torch.backends.cudnn.benchmark = False
-    print("channels_last weights, no benchmark ms", timeit(lambda: m.decode(z)))
-    # per-op profile of the fastest
-    from torch.profiler import profile, ProfilerActivity
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    print("decode of 4 images, ms:", timeit(lambda: m.decode(z)))
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
         m.decode(z); torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=70))
+    print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=48,
+                                                             max_shapes_column_width=70))
