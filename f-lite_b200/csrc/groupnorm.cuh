@@ -84,9 +84,8 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
     const long long total = hw * chunks;
     const uint4* xin = reinterpret_cast<const uint4*>(x + ((long long)n * hw) * C);
     uint4* yout = reinterpret_cast<uint4*>(y + ((long long)n * hw) * C);
-    for (long long i = (long long)blockIdx.x * GN_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * GN_THREADS) {
+    auto norm_chunk = [&](long long i, const uint4& v) {
         const int c = (int)(i % chunks);
-        const uint4 v = __ldcg(xin + i);
         const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma) + c);
         const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta) + c);
         const int g0 = (8 * c) / cpg, g1 = (8 * c + 4) / cpg;
@@ -102,8 +101,16 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __res
             if (apply_silu) { a = silu_f(a); b = silu_f(b); }
             o[j] = pack_bf16x2(a, b);
         }
-        yout[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        __stcs(yout + i, make_uint4(o[0], o[1], o[2], o[3]));       // written once, read next by a cuDNN kernel
+    };
+    const long long stride = (long long)gridDim.x * GN_THREADS;
+    long long i = (long long)blockIdx.x * GN_THREADS + threadIdx.x;
+    for (; i + 3 * stride < total; i += 4 * stride) {           // four independent 16-byte loads in flight per thread
+        const uint4 v0 = __ldcs(xin + i), v1 = __ldcs(xin + i + stride), v2 = __ldcs(xin + i + 2 * stride),
+                    v3 = __ldcs(xin + i + 3 * stride);
+        norm_chunk(i, v0); norm_chunk(i + stride, v1); norm_chunk(i + 2 * stride, v2); norm_chunk(i + 3 * stride, v3);
     }
+    for (; i < total; i += stride) norm_chunk(i, __ldcs(xin + i));
 }
 
 // y[N*HW, C] (channels-last, bf16) += bias[C]  [then y = residual + y], in place, 16 bytes per thread per step.
