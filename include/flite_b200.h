@@ -71,7 +71,7 @@ extern "C" {
 #define FLITE_TUNE_GEMM_HINT_A 9      /* L2 eviction hint of the GEMM's A-tile TMA loads: 0 auto | 1 none | 2 evict_first | 3 evict_last */
 #define FLITE_TUNE_GEMM_HINT_B 10     /* same for the W-tile loads */
 #define FLITE_TUNE_PATCH_EMBED 11     /* 0 auto: patchify = gather + tcgen05 GEMM when C*P*P % 64 == 0 | 1 CUDA-core patch_embed kernel */
-#define FLITE_TUNE_ATTN_VARIANT_SHORT_K 12 /* attention variant for FLITE_ATTN_AUTO calls with <= 512 keys per sequence on average (cross-attention); 0 = same as the long-key default; 9 (FLITE_ATTN_XRES) = the host model requests the resident-K/V kernel when the padded context has <= 256 tokens (opt-in) */
+#define FLITE_TUNE_ATTN_VARIANT_SHORT_K 12 /* attention variant for FLITE_ATTN_AUTO calls with <= 512 keys per sequence on average (cross-attention); 0 = same as the long-key default (the persistent kernel); 9 (FLITE_ATTN_XRES) = the host model requests the round-1 resident-K/V kernel when the padded context has <= 256 tokens (A/B only: slower than the default now) */
 #define FLITE_TUNE_P2P_TIMEOUT_S 13    /* seconds a cross-rank flag wait (flite_p2p_wait) may spin before it aborts; 0 = default 120 */
 #define FLITE_TUNE_GEMM_NARROW_M 14    /* 0 = a last M-tile with <= 128 valid rows runs as M = 128 MMAs (default), 1 = padded 256-row tile */
 #define FLITE_TUNE_ATTN_SK_MODE 15     /* schedule of flite_attention_streamk: 0 = stream-K shares | 1 = whole units round-robin (persistent, never splits a unit) | 2 = hybrid (whole rounds in lock step, stream-K over the last 1..2 units per cluster) */
@@ -195,16 +195,21 @@ int flite_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
 
 /* Varlen non-causal flash attention, head_dim 256.                                        model.py:203-211
  *   q[rows_q, ldq] head h at columns q_col0 + 256 h (same for k, v); cu_q / cu_k int32 [B+1] on device;
- *   out[rows_q, ldo] head-major columns; max_q = longest query sequence (host value). */
+ *   out[rows_q, ldo] head-major columns; max_q = longest query sequence (host value).
+ *   variant FLITE_ATTN_AUTO = FLITE_ATTN_PERSISTENT: one wave of 2-CTA clusters walks whole (sequence, head, 256-query
+ *   tile) units round-robin with the per-sequence lengths of cu_q / cu_k (bit-identical to variant 5, one cluster per
+ *   unit); whole 128-row output tiles leave through shared memory + TMA stores when `out` is 16-byte aligned. */
 int flite_attention_varlen(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
                            int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out,
                            int64_t ldo, const int* cu_q, const int* cu_k, int B, int H, int max_q,
                            float softmax_scale, int variant, void* stream);
 
 /* Same attention for UNIFORM sequence lengths (every sequence q_len queries / k_len keys -- the DiT's image stream),
- * as ONE persistent wave of 2-CTA clusters with stream-K work shares: units x key-tiles are cut into equal contiguous
- * shares, a unit split between two clusters is merged through `workspace` (flite_attention_streamk_workspace_bytes()
- * bytes, 16-byte aligned, zero-filled ONCE by the caller when allocated; the kernel leaves it zeroed).   model.py:203-211 */
+ * as ONE persistent wave of 2-CTA clusters; FLITE_TUNE_ATTN_SK_MODE picks the schedule: 1 = whole units round-robin
+ * (what flite_b200.DiT uses: never splits a unit, bit-identical to flite_attention_varlen), 0 = stream-K work shares
+ * (units x key-tiles cut into equal contiguous shares), 2 = hybrid (whole rounds, then shares of 1..2 units).  A unit
+ * split between two clusters is merged through `workspace` (flite_attention_streamk_workspace_bytes() bytes, 16-byte
+ * aligned, zero-filled ONCE by the caller when allocated; the kernel leaves it zeroed).                model.py:203-211 */
 int64_t flite_attention_streamk_workspace_bytes(void);
 int flite_attention_streamk(const void* q, int64_t ldq, int64_t rows_q, int q_col0, const void* k, int64_t ldk,
                             int64_t rows_k, int k_col0, const void* v, int64_t ldv, int v_col0, void* out,
